@@ -1,0 +1,124 @@
+"""Host-side mirror of the reference's problem/result types.
+
+  PDMPProblem   reference src/problem.jl:132-193 (constructors :168-193)
+  PDMPResult    reference src/utils.jl:66-79
+  EnsembleResult  ensemble analogue: CSR-ragged saved points + per-trajectory counters +
+                  on-GPU statistics (the reference has no ensemble API)
+"""
+from dataclasses import dataclass, field
+from typing import Any, Optional, Tuple
+
+import numpy as np
+
+from . import _abi
+
+
+def _delta_dummy(xc, xd, parms, t, ind_reaction):  # reference src/jumps.jl:4-6
+    return None
+
+
+class PDMPProblem:
+    """PDMPProblem(F, R, [Delta], nu, xc0, xd0, parms, tspan)  — reference src/problem.jl:168-193.
+
+    F, R, Delta are kept for API parity (Julia closures cannot cross to the device; the
+    device functor is chosen by the algorithm: ``CHVGPU(model)``).  They may be Python
+    callables with the reference signatures, model names, or None.
+
+    Constructors mirrored:
+      PDMPProblem(F, R, Delta, nu, xc0, xd0, parms, tspan)
+      PDMPProblem(F, R, nu, xc0, xd0, parms, tspan)
+      PDMPProblem(F, R, Delta, reaction_number:int, xc0, xd0, parms, tspan)  (all-zero nu)
+    """
+
+    def __init__(self, F, R, *args):
+        if len(args) == 5:
+            Delta = _delta_dummy
+            nu, xc0, xd0, parms, tspan = args
+        elif len(args) == 6:
+            Delta, nu, xc0, xd0, parms, tspan = args
+        else:
+            raise TypeError("PDMPProblem: expected (F,R,nu,xc0,xd0,parms,tspan) or "
+                            "(F,R,Delta,nu,xc0,xd0,parms,tspan)")
+        self.F, self.R, self.Delta = F, R, Delta
+        self.xc0 = np.array(xc0, dtype=np.float64).reshape(-1)
+        self.xd0 = np.array(xd0, dtype=np.int64).reshape(-1)
+        if isinstance(nu, (int, np.integer)):  # reaction_number form, src/problem.jl:190-193
+            nu = np.zeros((int(nu), self.xd0.size), dtype=np.int64)
+        self.nu = np.ascontiguousarray(np.array(nu, dtype=np.int64))
+        if self.nu.ndim != 2 or self.nu.shape[1] != self.xd0.size:
+            raise ValueError("nu must be [n_reactions x length(xd0)]")
+        self.parms = np.array(parms, dtype=np.float64).reshape(-1)
+        ti, tf = tspan
+        self.tspan = [float(ti), float(tf)]  # mutable like the reference (src/problem.jl:135)
+
+    @property
+    def n_c(self):
+        return self.xc0.size
+
+    @property
+    def n_d(self):
+        return self.xd0.size
+
+    @property
+    def n_r(self):
+        return self.nu.shape[0]
+
+
+@dataclass
+class PDMPResult:
+    """One trajectory, laid out like the reference's PDMPResult (src/utils.jl:66-79):
+    xc is [n_c, K], xd is [n_d, K] (Julia column k = saved point k)."""
+    time: np.ndarray
+    xc: np.ndarray
+    xd: np.ndarray
+    rates: np.ndarray
+    save_positions: Tuple[bool, bool]
+    njumps: int
+    nrejected: int
+    status: int = 0
+
+
+@dataclass
+class EnsembleResult:
+    n_traj: int
+    n_c: int
+    n_d: int
+    offsets: np.ndarray            # [n_traj+1] uint64
+    time: np.ndarray               # [total]
+    xc: np.ndarray                 # [total, n_c]
+    xd: np.ndarray                 # [total, n_d] int64
+    njumps: np.ndarray             # [n_traj] int64
+    nrejected: np.ndarray          # [n_traj] int64
+    status: np.ndarray             # [n_traj] uint8
+    stat_count: np.ndarray         # [T, C]
+    stat_sum: np.ndarray
+    stat_sumsq: np.ndarray
+    hist: np.ndarray               # [T, H, B] uint64
+    counters: dict = field(default_factory=dict)
+    save_positions: Tuple[bool, bool] = (False, True)
+    sample_times: Optional[np.ndarray] = None
+    _keep: Any = None
+
+    def __len__(self):
+        return self.n_traj
+
+    def __getitem__(self, i) -> PDMPResult:
+        a, b = int(self.offsets[i]), int(self.offsets[i + 1])
+        return PDMPResult(self.time[a:b], self.xc[a:b].T, self.xd[a:b].T, np.empty(0),
+                          self.save_positions, int(self.njumps[i]), int(self.nrejected[i]),
+                          int(self.status[i]))
+
+    def mean(self):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return self.stat_sum / self.stat_count
+
+    def var(self):
+        """Unbiased sample variance per (sample time, component)."""
+        n = self.stat_count
+        with np.errstate(invalid="ignore", divide="ignore"):
+            m = self.stat_sum / n
+            return (self.stat_sumsq - n * m * m) / (n - 1.0)
+
+    def status_histogram(self):
+        c = np.bincount(self.status, minlength=len(_abi.STATUS_NAMES))
+        return {name: int(c[k]) for k, name in enumerate(_abi.STATUS_NAMES) if c[k]}
