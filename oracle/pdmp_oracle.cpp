@@ -467,9 +467,13 @@ struct Sampler {
     bool flow_to(double tau, const int64_t* xd, const double* p, uint64_t max_attempts, bool hairer, int* fs) {
         auto f = [&](double* dx, const double* x, double t) { M::F(dx, x, xd, p, t); };
         if (!(tau > aux.t)) return true;
-        if (!aux.has_dt) {
-            if (hairer) aux.init_dt(f, tau - aux.t);
-            else { aux.dt = tau - aux.t; aux.has_dt = true; }
+        if (hairer) {
+            if (!aux.has_dt) aux.init_dt(f, tau - aux.t);
+        } else {
+            // engine policy: every sub-flow first tries the whole interval in one step with a
+            // fresh controller (no state carried between sub-flows => fewer live registers on
+            // the GPU; the twin here does the same so that step sequences are comparable)
+            aux.dt = tau - aux.t; aux.qold = QOLDINIT; aux.has_dt = true;
         }
         return aux.advance_to(f, tau, max_attempts, fs);
     }

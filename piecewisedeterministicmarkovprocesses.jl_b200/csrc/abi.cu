@@ -1,0 +1,496 @@
+// abi.cu — the C ABI of libpdmp_b200.so (include/pdmp_b200.h): model registry, resident
+// ensemble handle, kernel launches, pool -> CSR compaction, host staging.
+//
+// Replaces the reference's per-trajectory `solve(problem, CHV(ode))` /
+// `solve(problem, Rejection(ode))` (src/chvdiffeq.jl:211-237, src/rejectiondiffeq.jl:155-176)
+// with one ensemble launch.  No CPU fallback: without a usable GPU every compute entry point
+// returns PDMP_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "ensemble_kernel.cuh"
+
+namespace pdmp {
+// one translation unit per model (parallel nvcc), collected here
+ModelEntry entry_tcp(int), entry_tcp2d(int), entry_morris_lecar(int), entry_sir_rejection(int), entry_sir(int),
+    entry_pdmp_stiff(int), entry_tcp_rejection(int), entry_pdmp_explosion(int), entry_neuron_eva(int);
+
+static const std::vector<ModelEntry>& registry() {
+    static const std::vector<ModelEntry> r = {
+        entry_tcp(0),           entry_tcp2d(1),         entry_morris_lecar(2),
+        entry_sir_rejection(3), entry_sir(4),           entry_pdmp_stiff(5),
+        entry_tcp_rejection(6), entry_pdmp_explosion(7), entry_neuron_eva(8)};
+    return r;
+}
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(PDMP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));              \
+    } while (0)
+
+// max records one trajectory can store: initial point + (pre + post) per threshold + final point
+static unsigned long long max_records_per_traj(const pdmp_solve_opts& o) {
+    const unsigned long long thr = (unsigned long long)std::max<long long>(o.n_jumps - 1, 0);
+    return 2ull + thr * (unsigned long long)((o.save_pre ? 1 : 0) + (o.save_post ? 1 : 0));
+}
+static int table_width(unsigned long long maxrec) {
+    unsigned long long cap = 0;
+    int k = 0;
+    while (cap < maxrec) { cap += seg_records(k); ++k; }
+    return std::max(k, 1);
+}
+static unsigned long long pool_records_for(unsigned long long nrec) {  // capacity a trajectory of nrec records uses
+    unsigned long long cap = 0;
+    int k = 0;
+    while (cap < nrec) { cap += seg_records(k); ++k; }
+    return cap;
+}
+
+template <class T>
+struct Pinned {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    ~Pinned() { if (p) cudaFreeHost(p); }
+};
+
+}  // namespace pdmp
+
+using namespace pdmp;
+
+struct pdmp_ensemble {
+    int device = 0;
+    const ModelEntry* m = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    pdmp_solve_opts o{};
+    unsigned long long n = 0;
+    KParams P{};
+    bool records = false, stats = false;
+    int grid = 0;
+    size_t smem = 0;
+    // device buffers
+    double* d_xc0 = nullptr; long long* d_xd0 = nullptr; double* d_replay = nullptr; double* d_sample = nullptr;
+    double* d_stats = nullptr; unsigned long long* d_hist = nullptr; unsigned long long* d_ctl = nullptr;
+    unsigned char* d_pool = nullptr; unsigned int* d_segtab = nullptr;
+    unsigned long long* d_nrec = nullptr;  // [n+1], last = 0 (so the scan yields the total)
+    long long* d_njumps = nullptr; long long* d_nrej = nullptr; unsigned char* d_status = nullptr;
+    unsigned long long* d_offsets = nullptr; double* d_time = nullptr; double* d_xc = nullptr; long long* d_xd = nullptr;
+    void* d_scan = nullptr; size_t scan_bytes = 0;
+    unsigned long long csr_cap = 0;
+    size_t n_stats = 0, n_hist = 0;
+    // host staging (pinned)
+    Pinned<unsigned long long> h_offsets, h_hist, h_ctl;
+    Pinned<double> h_time, h_xc, h_stats;
+    Pinned<long long> h_xd, h_njumps, h_nrej;
+    Pinned<unsigned char> h_status;
+    bool ran = false;
+    float ms_kernel = 0, ms_compact = 0;
+    double ms_h2d = 0, ms_d2h = 0;
+    cudaStream_t last_stream = nullptr;
+
+    ~pdmp_ensemble() {
+        cudaSetDevice(device);
+        void* bufs[] = {d_xc0, d_xd0, d_replay, d_sample, d_stats, d_hist, d_ctl, d_pool, d_segtab, d_nrec,
+                        d_njumps, d_nrej, d_status, d_offsets, d_time, d_xc, d_xd, d_scan};
+        for (void* b : bufs) if (b) cudaFree(b);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+// d_ctl layout (unsigned long long): [0] work cursor, [1] block cursor, [2..2+CT_N) counters
+enum { CTL_CURSOR = 0, CTL_BLK = 1, CTL_CT = 2, CTL_N = 2 + CT_N };
+
+extern "C" {
+
+int32_t pdmp_abi_version(void) { return PDMP_ABI_VERSION; }
+const char* pdmp_last_error(void) { return g_err.c_str(); }
+
+int32_t pdmp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int32_t pdmp_model_count(void) { return (int32_t)registry().size(); }
+int32_t pdmp_model_info_by_id(int32_t id, pdmp_model_info* out) {
+    if (!out || id < 0 || id >= (int)registry().size()) return fail(PDMP_ERR_MODEL, "unknown model id");
+    *out = registry()[id].info;
+    return PDMP_OK;
+}
+int32_t pdmp_model_lookup(const char* name, pdmp_model_info* out) {
+    if (!name || !out) return fail(PDMP_ERR_INVALID, "null argument");
+    for (const auto& e : registry())
+        if (std::strcmp(e.info.name, name) == 0) { *out = e.info; return PDMP_OK; }
+    return fail(PDMP_ERR_MODEL, std::string("unknown model '") + name + "'");
+}
+
+int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_ensemble** out) {
+    if (!d || !o || !out) return fail(PDMP_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (d->model_id < 0 || d->model_id >= (int)registry().size()) return fail(PDMP_ERR_MODEL, "unknown model id");
+    const ModelEntry& m = registry()[d->model_id];
+    const int NC = m.info.n_c, ND = m.info.n_d, NR = m.info.n_r;
+    if (o->n_jumps < 1) return fail(PDMP_ERR_INVALID, "n_jumps must be >= 1 and finite");
+    if (!(o->reltol > 0) || !(o->abstol > 0)) return fail(PDMP_ERR_INVALID, "reltol and abstol must be > 0");
+    if (d->n_parms < m.info.n_parms || d->n_parms > MAXP)
+        return fail(PDMP_ERR_MODEL, std::string("model '") + m.info.name + "' reads " +
+                                        std::to_string(m.info.n_parms) + " parameters");
+    if (!d->xc0 || !d->xd0 || !d->nu || (!d->parms && d->n_parms)) return fail(PDMP_ERR_INVALID, "null problem array");
+    if (o->algorithm != PDMP_ALG_CHV && o->algorithm != PDMP_ALG_REJECTION) return fail(PDMP_ERR_INVALID, "algorithm");
+    if (o->algorithm == PDMP_ALG_REJECTION && !m.info.has_bound)
+        return fail(PDMP_ERR_MODEL, std::string("model '") + m.info.name + "' has no rate bound: Rejection unavailable");
+    if (o->ode != PDMP_ODE_DP5 && o->ode != PDMP_ODE_TSIT5) return fail(PDMP_ERR_INVALID, "ode");
+    if (o->precision != PDMP_PREC_FP64) return fail(PDMP_ERR_UNSUPPORTED, "only FP64 is built in this version");
+    if (o->rng_mode == PDMP_RNG_REPLAY && (!o->replay_u || !o->replay_stride)) return fail(PDMP_ERR_INVALID, "replay_u");
+    if (o->hist_n < 0 || o->hist_n > MAXH) return fail(PDMP_ERR_INVALID, "hist_n must be <= 4");
+    if (o->hist_n && o->hist_bins < 1) return fail(PDMP_ERR_INVALID, "hist_bins");
+    if (d->n_traj > 0xfffffff0ull) return fail(PDMP_ERR_INVALID, "n_traj per call must be < 2^32");
+    if (pdmp_device_count() <= o->device || o->device < 0)
+        return fail(PDMP_ERR_NO_DEVICE, "no usable CUDA device (this engine has no CPU fallback)");
+    CK(cudaSetDevice(o->device));
+
+    auto* e = new pdmp_ensemble();
+    std::unique_ptr<pdmp_ensemble> guard(e);
+    e->device = o->device; e->m = &m; e->o = *o; e->n = d->n_traj;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (auto& v : e->ev) CK(cudaEventCreate(&v));
+    const unsigned long long n = d->n_traj;
+    KParams& P = e->P;
+    P.n_traj = n; P.traj_id_offset = d->traj_id_offset;
+    P.xc0_per_traj = d->xc0_per_traj; P.xd0_per_traj = d->xd0_per_traj;
+    for (int i = 0; i < MAXP; ++i) P.parms[i] = i < d->n_parms ? d->parms[i] : 0.0;
+    for (int r = 0; r < NR; ++r)
+        for (int c = 0; c < ND; ++c) {
+            const long long v = d->nu_col_major ? d->nu[(size_t)c * NR + r] : d->nu[(size_t)r * ND + c];
+            P.nu[r * ND + c] = (int)v;
+        }
+    P.t0 = d->t0; P.tf = d->tf;
+    P.reltol = o->reltol; P.abstol = o->abstol;
+    P.n_jumps = o->n_jumps;
+    P.max_attempts = o->max_attempts > 0 ? o->max_attempts : 1000000ll;
+    P.save_pre = o->save_pre; P.save_post = o->save_post; P.tstop_policy = o->tstop_policy;
+    P.rng_mode = o->rng_mode; P.seed = o->seed; P.replay_stride = o->replay_stride;
+    P.n_sample = o->n_sample_times; P.n_comp = NC + ND; P.hist_n = o->hist_n; P.hist_bins = o->hist_n ? o->hist_bins : 0;
+    e->records = !o->no_records;
+    e->stats = o->n_sample_times > 0;
+
+    // inputs
+    const size_t nxc = (size_t)(d->xc0_per_traj ? n : 1) * NC, nxd = (size_t)(d->xd0_per_traj ? n : 1) * ND;
+    CK(cudaMalloc(&e->d_xc0, std::max<size_t>(n, 1) * NC * sizeof(double)));
+    CK(cudaMalloc(&e->d_xd0, std::max<size_t>(n, 1) * ND * sizeof(long long)));
+    CK(cudaMemcpyAsync(e->d_xc0, d->xc0, nxc * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_xd0, d->xd0, nxd * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    P.xc0 = e->d_xc0; P.xd0 = e->d_xd0;
+    if (o->rng_mode == PDMP_RNG_REPLAY) {
+        const size_t nr = (size_t)n * o->replay_stride;
+        CK(cudaMalloc(&e->d_replay, std::max<size_t>(nr, 1) * sizeof(double)));
+        CK(cudaMemcpyAsync(e->d_replay, o->replay_u, nr * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        P.replay_u = e->d_replay;
+    }
+    if (e->stats) {
+        if (!o->sample_times) return fail(PDMP_ERR_INVALID, "sample_times is null");
+        for (int i = 0; i < o->n_sample_times; ++i) {
+            const double t = o->sample_times[i];
+            if (!(t > d->t0) || !(t <= d->tf) || (i && !(t > o->sample_times[i - 1])))
+                return fail(PDMP_ERR_INVALID, "sample_times must be increasing and within (t0, tf]");
+        }
+        CK(cudaMalloc(&e->d_sample, o->n_sample_times * sizeof(double)));
+        CK(cudaMemcpyAsync(e->d_sample, o->sample_times, o->n_sample_times * sizeof(double), cudaMemcpyHostToDevice,
+                           e->stream));
+        P.sample_times = e->d_sample;
+        for (int h = 0; h < o->hist_n; ++h) {
+            if (o->hist_comp[h] < 0 || o->hist_comp[h] >= NC + ND || !(o->hist_hi[h] > o->hist_lo[h]))
+                return fail(PDMP_ERR_INVALID, "histogram spec");
+            P.hist_comp[h] = o->hist_comp[h];
+            P.hist_lo[h] = o->hist_lo[h];
+            P.hist_scale[h] = (double)o->hist_bins / (o->hist_hi[h] - o->hist_lo[h]);
+        }
+    } else {
+        P.hist_n = 0; P.hist_bins = 0;
+    }
+    e->n_stats = (size_t)3 * P.n_sample * P.n_comp;
+    e->n_hist = (size_t)P.n_sample * P.hist_n * P.hist_bins;
+    CK(cudaMalloc(&e->d_stats, std::max<size_t>(e->n_stats, 1) * sizeof(double)));
+    CK(cudaMalloc(&e->d_hist, std::max<size_t>(e->n_hist, 1) * sizeof(unsigned long long)));
+    P.stats = e->d_stats; P.hist = e->d_hist;
+    const size_t smem_need = e->n_stats * sizeof(double) + e->n_hist * sizeof(unsigned);
+    P.stats_in_smem = e->stats && smem_need <= 40 * 1024;
+    e->smem = P.stats_in_smem ? smem_need : 0;
+
+    CK(cudaMalloc(&e->d_ctl, CTL_N * sizeof(unsigned long long)));
+    P.cursor = e->d_ctl + CTL_CURSOR; P.blk_cursor = e->d_ctl + CTL_BLK; P.counters = e->d_ctl + CTL_CT;
+    CK(cudaMalloc(&e->d_nrec, (n + 1) * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(e->d_nrec, 0, (n + 1) * sizeof(unsigned long long), e->stream));
+    CK(cudaMalloc(&e->d_njumps, std::max<size_t>(n, 1) * sizeof(long long)));
+    CK(cudaMalloc(&e->d_nrej, std::max<size_t>(n, 1) * sizeof(long long)));
+    CK(cudaMalloc(&e->d_status, std::max<size_t>(n, 1)));
+    P.nrec = e->d_nrec; P.njumps = e->d_njumps; P.nrejected = e->d_nrej; P.status = e->d_status;
+
+    // record pool + CSR
+    if (e->records) {
+        const unsigned long long maxrec = max_records_per_traj(*o);
+        P.table_w = table_width(maxrec);
+        const size_t rec_bytes = (size_t)m.rec_words * 8;
+        const size_t csr_bytes = (size_t)8 * (1 + NC + ND);
+        unsigned long long want = o->max_records;
+        const unsigned long long worst = n * pool_records_for(maxrec);
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t fixed = (size_t)n * P.table_w * 4 + (n + 1) * 16 + (64u << 20);
+        if (want == 0) {
+            const size_t budget = free_b > fixed ? (size_t)((free_b - fixed) * 0.85) : 0;
+            want = std::min<unsigned long long>(worst, budget / (rec_bytes + csr_bytes));
+        }
+        want = std::min(std::max<unsigned long long>(want, std::min<unsigned long long>(worst, n * REC_BLOCK)), worst);
+        P.pool_blocks = (want + REC_BLOCK - 1) / REC_BLOCK;
+        const size_t pool_bytes = (size_t)P.pool_blocks * REC_BLOCK * rec_bytes;
+        e->csr_cap = P.pool_blocks * REC_BLOCK;
+        if (pool_bytes + e->csr_cap * csr_bytes + fixed > free_b)
+            return fail(PDMP_ERR_CAPACITY, "record pool + CSR (" + std::to_string((pool_bytes + e->csr_cap * csr_bytes) >> 20) +
+                                               " MiB) exceed free device memory; lower max_records or shard the ensemble");
+        CK(cudaMalloc(&e->d_pool, std::max<size_t>(pool_bytes, 16)));
+        CK(cudaMalloc(&e->d_segtab, std::max<size_t>((size_t)n * P.table_w, 1) * sizeof(unsigned)));
+        CK(cudaMalloc(&e->d_offsets, (n + 1) * sizeof(unsigned long long)));
+        CK(cudaMalloc(&e->d_time, std::max<size_t>(e->csr_cap, 1) * sizeof(double)));
+        CK(cudaMalloc(&e->d_xc, std::max<size_t>(e->csr_cap * NC, 1) * sizeof(double)));
+        CK(cudaMalloc(&e->d_xd, std::max<size_t>(e->csr_cap * ND, 1) * sizeof(long long)));
+        P.pool = e->d_pool; P.seg_table = e->d_segtab;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, e->scan_bytes, e->d_nrec, e->d_offsets, (long long)(n + 1), e->stream));
+        CK(cudaMalloc(&e->d_scan, std::max<size_t>(e->scan_bytes, 16)));
+    } else {
+        P.table_w = 1; P.pool_blocks = 0;
+    }
+
+    // persistent launch shape: resident CTAs per SM x SM count, capped by the work
+    int bps = 0, sms = 0;
+    CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, e->smem, &bps));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+    if (bps < 1) return fail(PDMP_ERR_CUDA, "kernel does not fit on an SM");
+    const unsigned long long need_blocks = (n + BLOCK - 1) / BLOCK;
+    e->grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)bps * sms, need_blocks));
+    CK(cudaStreamSynchronize(e->stream));  // inputs are borrowed only for the duration of the call
+    *out = guard.release();
+    return PDMP_OK;
+}
+
+int32_t pdmp_ensemble_upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc0_per_traj, const int64_t* xd0,
+                                 int32_t xd0_per_traj) {
+    if (!e) return fail(PDMP_ERR_INVALID, "null ensemble");
+    CK(cudaSetDevice(e->device));
+    const int NC = e->m->info.n_c, ND = e->m->info.n_d;
+    if (xc0) {
+        CK(cudaMemcpyAsync(e->d_xc0, xc0, (size_t)(xc0_per_traj ? e->n : 1) * NC * sizeof(double),
+                           cudaMemcpyHostToDevice, e->stream));
+        e->P.xc0_per_traj = xc0_per_traj;
+    }
+    if (xd0) {
+        CK(cudaMemcpyAsync(e->d_xd0, xd0, (size_t)(xd0_per_traj ? e->n : 1) * ND * sizeof(long long),
+                           cudaMemcpyHostToDevice, e->stream));
+        e->P.xd0_per_traj = xd0_per_traj;
+    }
+    return PDMP_OK;
+}
+
+int32_t pdmp_ensemble_run(pdmp_ensemble* e, uint64_t seed, void* stream) {
+    if (!e) return fail(PDMP_ERR_INVALID, "null ensemble");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    if (stream) CK(cudaStreamSynchronize(e->stream));  // pending uploads were queued on our own stream
+    e->last_stream = st;
+    e->P.seed = seed;
+    CK(cudaMemsetAsync(e->d_ctl, 0, CTL_N * sizeof(unsigned long long), st));
+    if (e->n_stats) CK(cudaMemsetAsync(e->d_stats, 0, e->n_stats * sizeof(double), st));
+    if (e->n_hist) CK(cudaMemsetAsync(e->d_hist, 0, e->n_hist * sizeof(unsigned long long), st));
+    CK(cudaEventRecord(e->ev[0], st));
+    if (e->n) CK(e->m->launch(e->o.algorithm, e->o.ode, e->records, e->stats, e->P, e->grid, e->smem, st));
+    CK(cudaEventRecord(e->ev[1], st));
+    if (e->records && e->n) {
+        CK(cub::DeviceScan::ExclusiveSum(e->d_scan, e->scan_bytes, e->d_nrec, e->d_offsets, (long long)(e->n + 1), st));
+        CK(e->m->compact(e->P, e->d_offsets, e->d_time, e->d_xc, e->d_xd, st));
+    }
+    CK(cudaEventRecord(e->ev[2], st));
+    e->ran = true;
+    return PDMP_OK;
+}
+
+static int fill_counters(pdmp_ensemble* e, pdmp_result* r) {
+    CK(cudaStreamSynchronize(e->last_stream ? e->last_stream : e->stream));
+    CK(e->h_ctl.reserve(CTL_N));
+    CK(cudaMemcpy(e->h_ctl.p, e->d_ctl, CTL_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaEventElapsedTime(&e->ms_kernel, e->ev[0], e->ev[1]));
+    CK(cudaEventElapsedTime(&e->ms_compact, e->ev[1], e->ev[2]));
+    std::memset(r, 0, sizeof(*r));
+    r->n_traj = e->n;
+    r->rk_attempts = e->h_ctl.p[CTL_CT + CT_ATTEMPTS];
+    r->rk_rejects = e->h_ctl.p[CTL_CT + CT_REJECTS];
+    r->aux_attempts = e->h_ctl.p[CTL_CT + CT_AUX];
+    r->total_jumps = e->h_ctl.p[CTL_CT + CT_JUMPS];
+    r->total_candidates = e->h_ctl.p[CTL_CT + CT_CANDS];
+    r->kernel_ms = e->ms_kernel; r->compact_ms = e->ms_compact;
+    r->n_sample_times = e->P.n_sample; r->n_comp = e->P.n_comp; r->hist_n = e->P.hist_n; r->hist_bins = e->P.hist_bins;
+    r->n_c = e->m->info.n_c; r->n_d = e->m->info.n_d;
+    r->records_needed = e->h_ctl.p[CTL_BLK] * REC_BLOCK;
+    if (e->records && e->n) {
+        unsigned long long total = 0;
+        CK(cudaMemcpy(&total, e->d_offsets + e->n, sizeof(total), cudaMemcpyDeviceToHost));
+        r->total_records = total;
+    }
+    return PDMP_OK;
+}
+
+int32_t pdmp_ensemble_counters(pdmp_ensemble* e, pdmp_result* r) {
+    if (!e || !r) return fail(PDMP_ERR_INVALID, "null argument");
+    if (!e->ran) return fail(PDMP_ERR_INVALID, "ensemble has not run");
+    CK(cudaSetDevice(e->device));
+    return fill_counters(e, r);
+}
+
+int32_t pdmp_ensemble_fetch(pdmp_ensemble* e, int32_t fetch_records, pdmp_result* r) {
+    if (!e || !r) return fail(PDMP_ERR_INVALID, "null argument");
+    if (!e->ran) return fail(PDMP_ERR_INVALID, "ensemble has not run");
+    CK(cudaSetDevice(e->device));
+    int rc = fill_counters(e, r);
+    if (rc) return rc;
+    const size_t n = e->n;
+    const int NC = e->m->info.n_c, ND = e->m->info.n_d;
+    cudaStream_t st = e->stream;
+    CK(cudaEventRecord(e->ev[3], st));
+    CK(e->h_njumps.reserve(n)); CK(e->h_nrej.reserve(n)); CK(e->h_status.reserve(n));
+    CK(e->h_stats.reserve(e->n_stats)); CK(e->h_hist.reserve(e->n_hist));
+    if (n) {
+        CK(cudaMemcpyAsync(e->h_njumps.p, e->d_njumps, n * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(e->h_nrej.p, e->d_nrej, n * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(e->h_status.p, e->d_status, n, cudaMemcpyDeviceToHost, st));
+    }
+    if (e->n_stats) CK(cudaMemcpyAsync(e->h_stats.p, e->d_stats, e->n_stats * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (e->n_hist) CK(cudaMemcpyAsync(e->h_hist.p, e->d_hist, e->n_hist * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    const bool recs = fetch_records && e->records && n;
+    const size_t total = recs ? (size_t)r->total_records : 0;
+    if (recs) {
+        CK(e->h_offsets.reserve(n + 1)); CK(e->h_time.reserve(total)); CK(e->h_xc.reserve(total * NC));
+        CK(e->h_xd.reserve(total * ND));
+        CK(cudaMemcpyAsync(e->h_offsets.p, e->d_offsets, (n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if (total) {
+            CK(cudaMemcpyAsync(e->h_time.p, e->d_time, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(e->h_xc.p, e->d_xc, total * NC * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(e->h_xd.p, e->d_xd, total * ND * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    {
+        cudaEvent_t done;
+        CK(cudaEventCreate(&done));
+        CK(cudaEventRecord(done, st));
+        CK(cudaEventSynchronize(done));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e->ev[3], done));
+        cudaEventDestroy(done);
+        e->ms_d2h = ms;
+    }
+    r->d2h_ms = e->ms_d2h;
+    r->njumps = (int64_t*)e->h_njumps.p; r->nrejected = (int64_t*)e->h_nrej.p; r->status = e->h_status.p;
+    r->stat_count = e->h_stats.p;
+    r->stat_sum = e->h_stats.p ? e->h_stats.p + e->n_stats / 3 : nullptr;
+    r->stat_sumsq = e->h_stats.p ? e->h_stats.p + 2 * (e->n_stats / 3) : nullptr;
+    r->hist = (uint64_t*)e->h_hist.p;
+    if (recs) {
+        r->offsets = (uint64_t*)e->h_offsets.p; r->time = e->h_time.p; r->xc = e->h_xc.p; r->xd = (int64_t*)e->h_xd.p;
+    } else {
+        r->total_records = e->records ? r->total_records : 0;
+    }
+    if (e->records && e->h_ctl.p[CTL_BLK] > e->P.pool_blocks)
+        return fail(PDMP_ERR_CAPACITY, "record pool exhausted: " + std::to_string(r->records_needed) +
+                                           " record slots needed, " + std::to_string(e->csr_cap) +
+                                           " available; truncated trajectories carry status OUTPUT_OVERFLOW");
+    return PDMP_OK;
+}
+
+int32_t pdmp_ensemble_stats_device(pdmp_ensemble* e, void** stats_f64, uint64_t* n_f64, void** hist_u64, uint64_t* n_u64) {
+    if (!e) return fail(PDMP_ERR_INVALID, "null ensemble");
+    if (stats_f64) *stats_f64 = e->d_stats;
+    if (n_f64) *n_f64 = e->n_stats;
+    if (hist_u64) *hist_u64 = e->d_hist;
+    if (n_u64) *n_u64 = e->n_hist;
+    return PDMP_OK;
+}
+
+void pdmp_ensemble_destroy(pdmp_ensemble* e) { delete e; }
+
+int32_t pdmp_solve_ensemble(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_result* r) {
+    if (!d || !o || !r) return fail(PDMP_ERR_INVALID, "null argument");
+    std::memset(r, 0, sizeof(*r));
+    pdmp_ensemble* e = nullptr;
+    int rc = pdmp_ensemble_create(d, o, &e);
+    if (rc) return rc;
+    rc = pdmp_ensemble_run(e, o->seed, nullptr);
+    if (rc) { delete e; return rc; }
+    rc = pdmp_ensemble_fetch(e, 1, r);
+    if (rc && rc != PDMP_ERR_CAPACITY) { delete e; std::memset(r, 0, sizeof(*r)); return rc; }
+    r->owner = e;  // the result views the ensemble's pinned staging
+    return rc;
+}
+
+void pdmp_result_free(pdmp_result* r) {
+    if (r && r->owner) { delete (pdmp_ensemble*)r->owner; std::memset(r, 0, sizeof(*r)); }
+}
+
+// ---- FP64 FMA peak probe ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_probe(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) out[0] = s;
+}
+
+int32_t pdmp_fp64_peak_tflops(int32_t device, double* tflops) {
+    if (!tflops) return fail(PDMP_ERR_INVALID, "null argument");
+    if (pdmp_device_count() <= device || device < 0) return fail(PDMP_ERR_NO_DEVICE, "no usable CUDA device");
+    CK(cudaSetDevice(device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double* d = nullptr;
+    CK(cudaMalloc(&d, 8));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int iters = 1 << 15, grid = sms * 8;
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(a));
+        dfma_probe<<<grid, 256>>>(d, iters);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        const double fl = 2.0 * 8 * (double)iters * grid * 256;
+        if (rep) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    *tflops = best;
+    return PDMP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// device_core.cuh — building blocks of the sm_100a ensemble kernels:
+//   * Philox4x32-10 counter RNG + per-trajectory uniform stream (replaces the reference's bare
+//     `rand()` calls on the global RNG: src/problem.jl:153, src/chvdiffeq.jl:71, src/utils.jl:47,
+//     src/rejectiondiffeq.jl:35-36)
+//   * Dormand-Prince 5(4) and Tsitouras 5(4) tableaus as compile-time constants
+//   * one adaptive RK attempt with everything in registers (replaces OrdinaryDiffEq's
+//     perform_step! called through SciMLBase.step!, reference call site src/chvdiffeq.jl:143)
+//   * the PI step-size controller (OrdinaryDiffEq PIController defaults), powers in FP32 like
+//     OrdinaryDiffEq's `fastpower`
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pdmp {
+
+#define PDMP_DEV __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------
+// fast FP64 reciprocal: MUFU.RCP64H seed + 2 Newton steps (4 DFMA), IEEE division only on
+// the rare out-of-range path.  <= 2 ulp; used for vector-field scaling and error weights,
+// never for quantities that decide a discrete outcome.
+// ---------------------------------------------------------------------------------------
+PDMP_DEV double rcp_fast(double x) {
+#ifdef PDMP_EXACT_DIV
+    return 1.0 / x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    const double ax = fabs(x);
+    if (!(ax > 1e-290 && ax < 1e290)) r = 1.0 / x;  // zero / inf / nan / denormal-range
+    return r;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  counter = (gid_lo, gid_hi, block, 0),
+// key = (seed_lo, seed_hi).  One call yields two 52-bit uniforms in (0,1): exactly one
+// CHV jump's worth (pfsample draw + next exponential).
+// ---------------------------------------------------------------------------------------
+PDMP_DEV void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0;
+        const uint32_t n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+PDMP_DEV double u01_from_bits(uint32_t hi, uint32_t lo) {
+    const unsigned long long m = ((unsigned long long)hi << 20) | (lo >> 12);  // 52 bits
+    return ((double)m + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+struct DrawStream {
+    uint32_t idx;     // draws consumed
+    double cache;     // second half of the last Philox block
+    PDMP_DEV void init() { idx = 0; cache = 0.0; }
+    // REPLAY: reads the host-provided stream; PHILOX: draw k = block k/2, half k%2
+    PDMP_DEV double next(int rng_mode, const double* __restrict__ replay, uint64_t replay_len, uint64_t gid,
+                         uint64_t seed, bool& exhausted) {
+        const uint32_t k = idx++;
+        if (rng_mode == 1) {
+            if (k >= replay_len) { exhausted = true; return 0.5; }
+            return __ldg(replay + k);
+        }
+        if (k & 1u) return cache;
+        uint32_t c0 = (uint32_t)gid, c1 = (uint32_t)(gid >> 32), c2 = k >> 1, c3 = 0u;
+        philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+        cache = u01_from_bits(c2, c3);
+        return u01_from_bits(c0, c1);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// Tableaus.  a(s, j): coefficient of k_{j+1} in stage s+2 (s = 0..5; s = 5 is the b row),
+// bt(j): b - bhat.  constexpr functions so that fully unrolled loops fold the zeros away.
+// ---------------------------------------------------------------------------------------
+struct TabDP5 {
+    static constexpr int ID = 0;
+    __host__ __device__ static constexpr double c(int i) {
+        constexpr double C[7] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
+        return C[i];
+    }
+    __host__ __device__ static constexpr double a(int s, int j) {
+        constexpr double A[6][6] = {
+            {1.0 / 5, 0, 0, 0, 0, 0},
+            {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+            {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+            {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+            {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+            {35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+        return A[s][j];
+    }
+    __host__ __device__ static constexpr double bt(int j) {
+        constexpr double B[7] = {71.0 / 57600, 0.0, -71.0 / 16695, 71.0 / 1920, -17253.0 / 339200, 22.0 / 525,
+                                 -1.0 / 40};
+        return B[j];
+    }
+};
+
+struct TabTsit5 {
+    static constexpr int ID = 1;
+    __host__ __device__ static constexpr double c(int i) {
+        constexpr double C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+        return C[i];
+    }
+    __host__ __device__ static constexpr double a(int s, int j) {
+        constexpr double A[6][6] = {
+            {0.161, 0, 0, 0, 0, 0},
+            {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+            {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+            {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+            {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383,
+             0},
+            {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081,
+             2.324710524099774}};
+        return A[s][j];
+    }
+    __host__ __device__ static constexpr double bt(int j) {
+        constexpr double B[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995,
+                                 -0.1447110071732629, 0.5823571654525552, -0.45808210592918697, 1.0 / 66.0};
+        return B[j];
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// One RK attempt of size h from (u, k1 = f(u)) : fills unew, k7 = f(unew) (FSAL) and returns
+// e2 = sum_i (err_i / (abstol + max(|u_i|,|unew_i|) reltol))^2  (EEst^2 * D).
+// All arrays are compile-time indexed: they live in registers.
+// ---------------------------------------------------------------------------------------
+template <class Tab, int D, class RHS>
+PDMP_DEV double rk_attempt(RHS&& f, const double (&u)[D], const double (&k1)[D], double t, double h,
+                           double (&unew)[D], double (&k7)[D], double reltol, double abstol) {
+    double k[7][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) k[0][i] = k1[i];
+#pragma unroll
+    for (int s = 1; s < 7; ++s) {
+        double us[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double acc = Tab::a(s - 1, 0) * k[0][i];
+#pragma unroll
+            for (int j = 1; j < s; ++j)
+                if (Tab::a(s - 1, j) != 0.0) acc = fma(Tab::a(s - 1, j), k[j][i], acc);
+            us[i] = fma(h, acc, u[i]);
+        }
+        if (s == 6) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) unew[i] = us[i];
+        }
+        f(us, k[s], t + Tab::c(s) * h);
+    }
+    double e2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double acc = Tab::bt(0) * k[0][i];
+#pragma unroll
+        for (int j = 1; j < 7; ++j)
+            if (Tab::bt(j) != 0.0) acc = fma(Tab::bt(j), k[j][i], acc);
+        const double sc = fma(fmax(fabs(u[i]), fabs(unew[i])), reltol, abstol);
+        const double r = (h * acc) * rcp_fast(sc);
+        e2 = fma(r, r, e2);
+        k7[i] = k[6][i];
+    }
+    return e2;
+}
+
+// ---------------------------------------------------------------------------------------
+// PI controller (OrdinaryDiffEq PIController defaults for order-5 pairs: beta1 = 7/50,
+// beta2 = 2/25, gamma = 9/10, qmin = 1/5, qmax = 10, qoldinit = 1e-4).  The powers are
+// evaluated in FP32 (MUFU lg2/ex2), as OrdinaryDiffEq's fastpower does.
+//   accept : h_next = h / q,  qold = max(EEst, 1e-4)
+//   reject : h_next = h / min(1/qmin, q11 / gamma)
+// Works on EEst^2 (= e2 / D) to skip the square root.
+// ---------------------------------------------------------------------------------------
+struct PIController {
+    float qold;
+    PDMP_DEV void init() { qold = 1e-4f; }
+    // returns the factor f such that h_next = h * f
+    PDMP_DEV double step(double EEst2, bool accept) {
+        const float e2 = (float)EEst2;
+        float q11, q;
+        if (e2 == 0.0f) { q11 = 0.0f; q = 0.1f; }
+        else {
+            const float l = __log2f(e2);                       // log2(EEst^2)
+            q11 = exp2f(0.5f * 0.14f * l);                     // EEst^beta1
+            q = q11 * exp2f(-0.08f * __log2f(qold));           // / qold^beta2
+            q = fmaxf(0.1f, fminf(5.0f, q * (1.0f / 0.9f)));
+        }
+        if (accept) {
+            qold = fmaxf(sqrtf(e2), 1e-4f);
+            return (double)__frcp_rn(q);
+        }
+        return (double)__frcp_rn(fminf(5.0f, q11 * (1.0f / 0.9f)));
+    }
+};
+
+}  // namespace pdmp

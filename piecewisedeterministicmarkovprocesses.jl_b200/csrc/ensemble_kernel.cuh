@@ -1,0 +1,646 @@
+// ensemble_kernel.cuh — the persistent ensemble kernel: one PDMP trajectory per thread, all
+// state in registers, finished lanes refilled from a global work cursor.
+//
+// Replaces, for N trajectories at once:
+//   CHV        chv_diffeq! + chvjump + (chv::CHV)(xdot,x,caract,t)   reference src/chvdiffeq.jl:6-16,24-74,76-170
+//   Rejection  rejection_diffeq! + rejectionjump                     reference src/rejectiondiffeq.jl:5-8,14-74,76-152
+//   init!      src/problem.jl:150-161      pfsample  src/utils.jl:46-57      affect!  src/jumps.jl:28-36
+//   saving     _push_time!/_push_xc!/_push_xd!  src/problem.jl:146-148
+//
+// Loop shape: every iteration each live lane performs exactly ONE adaptive RK attempt (so a
+// warp stays converged through the arithmetic-heavy part); lanes whose step landed on their
+// jump threshold then run the (short, divergent) jump section.  Lanes that finished their
+// trajectory pull the next one from the cursor with a warp-aggregated atomic.
+#pragma once
+#include <algorithm>
+
+#include "device_core.cuh"
+#include "../../include/pdmp_b200.h"
+
+namespace pdmp {
+
+constexpr int MAXP = 16, MAXR = 8, MAXD = 8, MAXH = 4;
+constexpr int BLOCK = 128;           // threads per CTA
+constexpr int REC_BLOCK = 16;        // records per pool block (allocation granule)
+
+// counters[] slots
+enum { CT_ATTEMPTS = 0, CT_REJECTS, CT_AUX, CT_JUMPS, CT_CANDS, CT_N };
+
+struct KParams {
+    // problem
+    unsigned long long n_traj, traj_id_offset;
+    const double* xc0;
+    const long long* xd0;
+    int xc0_per_traj, xd0_per_traj;
+    double parms[MAXP];
+    int nu[MAXR * MAXD];  // [r * ND + d]
+    double t0, tf;
+    // options
+    double reltol, abstol;
+    long long n_jumps, max_attempts;
+    int save_pre, save_post, tstop_policy, rng_mode;
+    unsigned long long seed;
+    const double* replay_u;
+    unsigned long long replay_stride;
+    // sampling / statistics
+    int n_sample, n_comp, hist_n, hist_bins;
+    const double* sample_times;
+    int hist_comp[MAXH];
+    double hist_lo[MAXH], hist_scale[MAXH];  // bin = floor((v - lo) * scale)
+    double* stats;                  // [3][T][C] count | sum | sumsq
+    unsigned long long* hist;       // [T][H][B]
+    int stats_in_smem;
+    // work queue + counters
+    unsigned long long* cursor;
+    unsigned long long* counters;   // [CT_N]
+    // record pool
+    unsigned char* pool;            // pool_blocks * REC_BLOCK records of REC_WORDS 8-byte words
+    unsigned long long pool_blocks;
+    unsigned long long* blk_cursor; // blocks handed out (keeps counting past capacity)
+    unsigned int* seg_table;        // [n_traj][table_w] first block of each segment
+    int table_w;
+    // per-trajectory outputs
+    unsigned long long* nrec;       // [n_traj + 1], records stored per trajectory
+    long long* njumps;
+    long long* nrejected;
+    unsigned char* status;
+};
+
+// record layout in the pool: 8-byte words [t, xc[0..NC), xd packed 2 x int32], padded to an
+// even word count so that every record is 16-byte aligned (vectorised stores)
+template <class M>
+struct RecLayout {
+    static constexpr int XD_WORDS = (M::ND + 1) / 2;
+    static constexpr int RAW = 1 + M::NC + XD_WORDS;
+    static constexpr int WORDS = (RAW + 1) & ~1;
+    static constexpr int BYTES = WORDS * 8;
+};
+
+// geometric segment sizes: segment k holds REC_BLOCK << (k >> 2) records (4 segments per doubling)
+__host__ __device__ inline unsigned seg_records(int k) { return (unsigned)REC_BLOCK << (k >> 2); }
+
+template <class M, class Tab, int ALG, bool RECORDS, bool STATS>
+struct Traj {
+    static constexpr int NC = M::NC, ND = M::ND, NR = M::NR;
+    static constexpr int D = (ALG == PDMP_ALG_CHV) ? NC + 1 : NC;
+    using RL = RecLayout<M>;
+
+    // ---- integrator state ----
+    double y[D];        // CHV: (xc, t) in the time-change variable s ; Rejection: xc in time t
+    double k1[D];       // FSAL
+    double s, tstop, h; // integration variable, next threshold, proposed step
+    PIController pi;
+    // ---- PDMP state ----
+    int xd[ND];
+    double tlast;       // reference `t` of the outer loop (time of the last threshold)
+    double xs[NC], ts;  // anchor of the plain-F flow: state/time at the last executed jump
+                        // (CHV: caract.xc ; Rejection: state at the last candidate)
+    long long simnj, nfict;
+    unsigned attempts;
+    DrawStream rng;
+    unsigned lid;       // local trajectory index
+    // ---- writer ----
+    unsigned nrec_stored, seg_left;
+    int seg_k;
+    unsigned long long wslot;  // next record slot in the pool
+    bool overflow;
+    int next_sample;
+
+    // ------------------------------------------------------------------------------
+    PDMP_DEV double draw(const KParams& P, bool& exhausted) {
+        return rng.next(P.rng_mode, P.replay_u + (size_t)lid * P.replay_stride, P.replay_stride,
+                        P.traj_id_offset + lid, P.seed, exhausted);
+    }
+
+    // (chv::CHV)(xdot, x, caract, t): (F, 1) / Rtot      reference src/chvdiffeq.jl:6-16
+    PDMP_DEV void field(const KParams& P, const double* x, double* dx, double t) const {
+        if constexpr (ALG == PDMP_ALG_CHV) {
+            if constexpr (M::HAS_CHV_FIELD) {
+                M::chv_field(dx, x, xd, P.parms);
+            } else {
+                const double tau = x[NC];
+                const double inv = rcp_fast(M::rtot(x, xd, P.parms, tau));
+                M::F(dx, x, xd, P.parms, tau);
+#pragma unroll
+                for (int i = 0; i < NC; ++i) dx[i] *= inv;
+                dx[NC] = inv;
+            }
+        } else {
+            M::F(dx, x, xd, P.parms, t);  // Rejection flow, reference src/rejectiondiffeq.jl:5-8
+        }
+    }
+
+    // ---- record pool writer ----------------------------------------------------------
+    PDMP_DEV void write_record(const KParams& P, double t, const double* xc) {
+        if constexpr (!RECORDS) return;
+        if (seg_left == 0) {
+            const unsigned nrecs = seg_records(seg_k);
+            const unsigned nblk = nrecs / REC_BLOCK;
+            const unsigned long long b = atomicAdd(P.blk_cursor, (unsigned long long)nblk);
+            if (b + nblk > P.pool_blocks || seg_k >= P.table_w) overflow = true;
+            if (!overflow) {
+                P.seg_table[(size_t)lid * P.table_w + seg_k] = (unsigned)b;
+                wslot = b * REC_BLOCK;
+            }
+            seg_left = nrecs;
+            ++seg_k;
+        }
+        --seg_left;
+        if (overflow) return;
+        double w[RL::WORDS];
+        w[0] = t;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) w[1 + i] = xc[i];
+#pragma unroll
+        for (int i = 0; i < RL::XD_WORDS; ++i) {
+            const int lo = xd[2 * i];
+            const int hi = (2 * i + 1 < ND) ? xd[2 * i + 1] : 0;
+            w[1 + NC + i] = __hiloint2double(hi, lo);
+        }
+#pragma unroll
+        for (int i = RL::RAW; i < RL::WORDS; ++i) w[i] = 0.0;
+        double2* dst = reinterpret_cast<double2*>(P.pool + wslot * RL::BYTES);
+#pragma unroll
+        for (int i = 0; i < RL::WORDS / 2; ++i) __stcs(dst + i, make_double2(w[2 * i], w[2 * i + 1]));
+        ++wslot;
+        ++nrec_stored;
+    }
+
+    // ---- statistics at a sample time -------------------------------------------------
+    PDMP_DEV void accumulate(const KParams& P, double* sstat, unsigned* shist, int j, const double* xc) {
+        if constexpr (!STATS) return;
+        const int C = P.n_comp, TC = P.n_sample * C;
+#pragma unroll
+        for (int c = 0; c < NC + ND; ++c) {
+            const double v = c < NC ? xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
+            double* base = P.stats_in_smem ? sstat : P.stats;
+            atomicAdd(base + j * C + c, 1.0);
+            atomicAdd(base + TC + j * C + c, v);
+            atomicAdd(base + 2 * TC + j * C + c, v * v);
+        }
+        for (int hh = 0; hh < P.hist_n; ++hh) {
+            const int c = P.hist_comp[hh];
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < NC + ND; ++q)
+                if (q == c) v = q < NC ? xc[q < NC ? q : 0] : (double)xd[q >= NC ? q - NC : 0];
+            const double fb = floor((v - P.hist_lo[hh]) * P.hist_scale[hh]);
+            int b = fb < 0.0 ? 0 : (fb >= (double)P.hist_bins ? P.hist_bins - 1 : (int)fb);
+            if (!(fb == fb)) b = 0;
+            const size_t at = ((size_t)j * P.hist_n + hh) * P.hist_bins + b;
+            if (P.stats_in_smem) atomicAdd(shist + at, 1u);
+            else atomicAdd(P.hist + at, 1ull);
+        }
+    }
+
+    // ---- plain-F flow of the anchor (xs, ts) to tau: sample times and the "last bit" ----
+    // reference src/chvdiffeq.jl:160-168 (one fresh ODE solve per call there; here an adaptive
+    // loop with the same pair and the user's tolerances, chained from the last anchor)
+    PDMP_DEV bool flow_anchor_to(const KParams& P, double tau, unsigned& aux_attempts, int& fail) {
+        if constexpr (M::ZERO_FLOW) { ts = tau; return true; }
+        if (!(tau > ts)) return true;
+        double hh = tau - ts;
+        PIController c2; c2.init();
+        double f1[NC];
+        M::F(f1, xs, xd, P.parms, ts);
+        auto rhs = [&](const double* x, double* dx, double t) { M::F(dx, x, xd, P.parms, t); };
+        const unsigned budget = (unsigned)min((long long)0x7fffffff, P.max_attempts);
+        while (ts < tau) {
+            bool clipped = false;
+            double step = hh;
+            if (step >= tau - ts) { step = tau - ts; clipped = true; }
+            double xn[NC], f7[NC];
+            const double e2 = rk_attempt<Tab, NC>(rhs, xs, f1, ts, step, xn, f7, P.reltol, P.abstol);
+            if (++aux_attempts > budget) { fail = PDMP_ST_MAX_ATTEMPTS; return false; }
+            if (!(e2 == e2) || isinf(e2)) { fail = PDMP_ST_NAN; return false; }
+            const bool accept = e2 <= (double)NC;
+            const double fac = c2.step(e2 * (1.0 / NC), accept);
+            if (accept) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) { xs[i] = xn[i]; f1[i] = f7[i]; }
+                double tn = ts + step;
+                if (clipped || fabs(tn - tau) < 100.0 * 2.220446049250313e-16 * fmax(fabs(tn), fabs(tau))) tn = tau;
+                ts = tn;
+            }
+            hh = step * fac;
+        }
+        return true;
+    }
+
+    PDMP_DEV bool sample_until(const KParams& P, double* sstat, unsigned* shist, double tlimit, unsigned& aux,
+                               int& fail) {
+        if constexpr (STATS) {
+            while (next_sample < P.n_sample) {
+                const double tau = __ldg(P.sample_times + next_sample);
+                if (!(tau <= tlimit)) break;
+                if (!flow_anchor_to(P, tau, aux, fail)) return false;
+                accumulate(P, sstat, shist, next_sample, xs);
+                ++next_sample;
+            }
+        }
+        return true;
+    }
+
+    // ---- init!(problem) + integrator construction --------------------------------------
+    // reference src/problem.jl:150-161, src/chvdiffeq.jl:97-136, src/rejectiondiffeq.jl:91-116
+    PDMP_DEV void init(const KParams& P, unsigned idx, bool& exhausted) {
+        lid = idx;
+        rng.init();
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            y[i] = P.xc0[(P.xc0_per_traj ? (size_t)idx * NC : 0) + i];
+            xs[i] = y[i];
+        }
+#pragma unroll
+        for (int i = 0; i < ND; ++i) xd[i] = (int)P.xd0[(P.xd0_per_traj ? (size_t)idx * ND : 0) + i];
+        const double E0 = -log(draw(P, exhausted));  // tstop_extended = -log(rand())
+        if constexpr (ALG == PDMP_ALG_CHV) {
+            y[NC] = P.t0;  // X_extended[end] = ti
+            s = 0.0;
+            tstop = E0;
+        } else {
+            s = P.t0;
+            tstop = E0 / M::bound(y, xd, P.parms, P.t0) + P.t0;  // src/rejectiondiffeq.jl:105-107
+        }
+        tlast = P.t0; ts = P.t0;
+        simnj = 1; nfict = 0;
+        attempts = 0;
+        nrec_stored = 0; seg_left = 0; seg_k = 0; wslot = 0; overflow = false;
+        next_sample = 0;
+        pi.init();
+        write_record(P, P.t0, xs);  // the initial point is always kept (resize!(..., 1))
+
+        // Hairer-Norsett-Wanner initial step (OrdinaryDiffEq ode_determine_initdt), order 5
+        field(P, y, k1, s);
+        double d0 = 0.0, d1 = 0.0;
+        double sk[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            sk[i] = P.abstol + fabs(y[i]) * P.reltol;
+            const double a = y[i] / sk[i], b = k1[i] / sk[i];
+            d0 = fma(a, a, d0); d1 = fma(b, b, d1);
+        }
+        d0 = sqrt(d0 * (1.0 / D)); d1 = sqrt(d1 * (1.0 / D));
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+        dt0 = fmin(dt0, 1e9);
+        double u1[D], f1[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) u1[i] = fma(dt0, k1[i], y[i]);
+        field(P, u1, f1, s + dt0);
+        double d2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) { const double a = (f1[i] - k1[i]) / sk[i]; d2 = fma(a, a, d2); }
+        d2 = sqrt(d2 * (1.0 / D)) / dt0;
+        const double dm = fmax(d1, d2);
+        const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) / 5.0);
+        h = fmin(fmin(100.0 * dt0, dt1), 1e9);
+    }
+
+    PDMP_DEV void finish(const KParams& P, int st) {
+        if (overflow && (st == PDMP_ST_OK || st == PDMP_ST_HIT_NJUMPS)) st = PDMP_ST_OUTPUT_OVERFLOW;
+        P.nrec[lid] = nrec_stored;
+        P.njumps[lid] = simnj;
+        P.nrejected[lid] = nfict;
+        P.status[lid] = (unsigned char)st;
+    }
+
+    // ---- loop epilogue shared by both algorithms: end-of-trajectory tests ----------------
+    // returns true when the trajectory is finished
+    PDMP_DEV bool epilogue(const KParams& P, bool rng_exhausted, unsigned& aux, int& fail) {
+        if (rng_exhausted) { finish(P, PDMP_ST_REPLAY_EXHAUSTED); return true; }
+        if (!(tlast < P.tf)) {  // while (t < tf) ...
+            if (tlast > P.tf) {  // last bit
+                if (!flow_anchor_to(P, P.tf, aux, fail)) { finish(P, fail); return true; }
+                write_record(P, P.tf, xs);
+            }
+            finish(P, PDMP_ST_OK);
+            return true;
+        }
+        if (!(simnj < P.n_jumps)) { finish(P, PDMP_ST_HIT_NJUMPS); return true; }
+        return false;
+    }
+
+    // ---- chvjump, reference src/chvdiffeq.jl:24-74, and the tail of the while body :145-157 ----
+    PDMP_DEV bool chv_threshold(const KParams& P, double* sstat, unsigned* shist, unsigned& aux,
+                                unsigned& jumps) {
+        int fail = PDMP_ST_OK;
+        bool ex = false;
+        const double tj = y[NC];
+        if (!sample_until(P, sstat, shist, fmin(tj, P.tf), aux, fail)) { finish(P, fail); return true; }
+        if (P.save_pre && tj <= P.tf) write_record(P, tj, y);  // :41-48
+        double rate[NR];
+        M::rates(rate, y, xd, P.parms, tj);  // :51, rates at the PRE-jump state
+        double tot = rate[0];
+#pragma unroll
+        for (int i = 1; i < NR; ++i) tot += rate[i];  // sum(rate), left to right
+        if (!(tot > 0.0) || isinf(tot)) { finish(P, PDMP_ST_NONPOSITIVE_RATE); return true; }
+        if (tj < P.tf) {  // :52
+            // pfsample, reference src/utils.jl:46-57 (strict <, last index absorbs round-off)
+            const double thr = draw(P, ex) * tot;
+            int ev = 1;
+            double cw = rate[0];
+#pragma unroll
+            for (int i = 1; i < NR; ++i)
+                if (ev == i && cw < thr) { ev = i + 1; cw += rate[i]; }
+            // affect!, reference src/jumps.jl:28-36
+#pragma unroll
+            for (int i = 0; i < ND; ++i) xd[i] += P.nu[(ev - 1) * ND + i];
+            if constexpr (M::HAS_DELTA) M::delta(y, xd, P.parms, tj, ev);
+            field(P, y, k1, s);  // u_modified!(integrator, true): FSAL re-evaluated
+#pragma unroll
+            for (int i = 0; i < NC; ++i) xs[i] = y[i];  // caract.xc .= u
+            ts = tj;
+            ++jumps;
+        }
+        ++simnj;                          // :70
+        tstop += -log(draw(P, ex));       // :71, always drawn
+        if (!(tlast < tj)) { finish(P, PDMP_ST_NO_PROGRESS); return true; }  // @assert :145
+        tlast = tj;                       // :146
+        if (P.save_post && tj <= P.tf) write_record(P, tj, xs);  // :149-156
+        return epilogue(P, ex, aux, fail);
+    }
+
+    // ---- rejectionjump, reference src/rejectiondiffeq.jl:14-74, and :121-139 ----
+    PDMP_DEV bool rej_candidate(const KParams& P, double* sstat, unsigned* shist, unsigned& aux,
+                                unsigned& jumps) {
+        int fail = PDMP_ST_OK;
+        bool ex = false;
+        const double tc = s;
+        if (!sample_until(P, sstat, shist, fmin(tc, P.tf), aux, fail)) { finish(P, fail); return true; }
+        double rate[NR];
+        M::rates(rate, y, xd, P.parms, tc);
+        double tot = rate[0];
+#pragma unroll
+        for (int i = 1; i < NR; ++i) tot += rate[i];
+        const double bnd = M::bound(y, xd, P.parms, tc);
+        if (!(tot < bnd)) { finish(P, PDMP_ST_BOUND_VIOLATED); return true; }  // @assert :33
+        const bool reject = draw(P, ex) < 1.0 - tot / bnd;   // :35
+        const double dtn = -log(draw(P, ex)) / bnd;          // :36
+        const bool fire = tc < P.tf && !reject;
+        if (fire) {                                          // :41
+            const double thr = draw(P, ex) * tot;            // :55
+            int ev = 1;
+            double cw = rate[0];
+#pragma unroll
+            for (int i = 1; i < NR; ++i)
+                if (ev == i && cw < thr) { ev = i + 1; cw += rate[i]; }
+#pragma unroll
+            for (int i = 0; i < ND; ++i) xd[i] += P.nu[(ev - 1) * ND + i];
+            if constexpr (M::HAS_DELTA) M::delta(y, xd, P.parms, tc, ev);
+            field(P, y, k1, s);
+            ++simnj;                                         // :64
+            ++jumps;
+        } else {
+            ++nfict;                                         // :66
+        }
+        if (tc < P.tf) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) xs[i] = y[i];
+            ts = tc;
+        }
+        tstop += dtn;                                        // :71
+        if (tlast >= tc) { finish(P, PDMP_ST_NO_PROGRESS); return true; }  // :121-124
+        tlast = tc;
+        if (P.save_post && tc <= P.tf && !reject) write_record(P, tc, y);  // :128-138
+        return epilogue(P, ex, aux, fail);
+    }
+};
+
+template <class M, class Tab, int ALG, bool RECORDS, bool STATS>
+__global__ void __launch_bounds__(BLOCK) ensemble_kernel(const __grid_constant__ KParams P) {
+    using T = Traj<M, Tab, ALG, RECORDS, STATS>;
+    constexpr int D = T::D;
+    extern __shared__ double smem[];
+    double* sstat = smem;
+    unsigned* shist = reinterpret_cast<unsigned*>(smem + 3 * P.n_sample * P.n_comp);
+    if (STATS && P.stats_in_smem) {
+        const int nd = 3 * P.n_sample * P.n_comp, nh = P.n_sample * P.hist_n * P.hist_bins;
+        for (int i = threadIdx.x; i < nd; i += BLOCK) sstat[i] = 0.0;
+        for (int i = threadIdx.x; i < nh; i += BLOCK) shist[i] = 0u;
+        __syncthreads();
+    }
+
+    T tr;
+    bool alive = false, exhausted = false;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned c_attempts = 0, c_rejects = 0, c_aux = 0, c_jumps = 0, c_cands = 0;
+    unsigned long long g_attempts = 0;  // spill-over of the 32-bit attempt counter
+    const unsigned budget = (unsigned)min((long long)0x7fffffff, P.max_attempts);
+
+    for (;;) {
+        // ---- refill finished lanes from the global cursor (warp-aggregated) ----
+        const unsigned need = __ballot_sync(0xffffffffu, !alive && !exhausted);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!alive && !exhausted) {
+                const unsigned long long idx = base + __popc(need & ((1u << lane) - 1u));
+                if (idx < P.n_traj) {
+                    bool ex = false;
+                    tr.init(P, (unsigned)idx, ex);
+                    alive = true;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !alive)) break;
+        if (!alive) continue;
+
+        // ---- one adaptive RK attempt, clipped at the threshold (tstops) ----
+        bool hit = false;
+        if (ALG == PDMP_ALG_REJECTION && M::ZERO_FLOW) {
+            // F = F_dummy: the flow is the identity, go straight to the candidate time
+            tr.s = tr.tstop;
+            hit = true;
+        } else {
+            const double hprop = tr.h;
+            double step = hprop;
+            bool clipped = false;
+            const double rem = tr.tstop - tr.s;
+            if (step >= rem) { step = rem; clipped = true; }
+            double yn[D], k7[D];
+            auto rhs = [&](const double* x, double* dx, double t) { tr.field(P, x, dx, t); };
+            const double e2 = rk_attempt<Tab, D>(rhs, tr.y, tr.k1, tr.s, step, yn, k7, P.reltol, P.abstol);
+            ++c_attempts;
+            if (!(e2 == e2) || isinf(e2)) { tr.finish(P, PDMP_ST_NAN); alive = false; continue; }
+            if (++tr.attempts > budget) { tr.finish(P, PDMP_ST_MAX_ATTEMPTS); alive = false; continue; }
+            const bool accept = e2 <= (double)D;
+            const double fac = tr.pi.step(e2 * (1.0 / D), accept);
+            double hnext = step * fac;
+            if (accept) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) { tr.y[i] = yn[i]; tr.k1[i] = k7[i]; }
+                double sn = tr.s + step;
+                if (clipped || fabs(sn - tr.tstop) < 100.0 * 2.220446049250313e-16 * fmax(fabs(sn), fabs(tr.tstop))) {
+                    sn = tr.tstop;
+                    hit = true;
+                }
+                tr.s = sn;
+                if (clipped && P.tstop_policy == 1) hnext = fmax(hnext, hprop);
+            } else {
+                ++c_rejects;
+            }
+            tr.h = hnext;
+        }
+        // ---- threshold reached: jump section (divergent, short) ----
+        if (hit) {
+            ++c_cands;
+            bool done;
+            if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, sstat, shist, c_aux, c_jumps);
+            else done = tr.rej_candidate(P, sstat, shist, c_aux, c_jumps);
+            if (done) alive = false;
+        }
+        if (c_attempts > 0x40000000u) { g_attempts += c_attempts; c_attempts = 0; }
+    }
+
+    // ---- flush counters (warp reduce, one atomic per warp) and CTA statistics ----
+    unsigned long long v[CT_N] = {g_attempts + c_attempts, c_rejects, c_aux, c_jumps, c_cands};
+#pragma unroll
+    for (int k = 0; k < CT_N; ++k) {
+        unsigned long long x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(P.counters + k, x);
+    }
+    if (STATS && P.stats_in_smem) {
+        __syncthreads();
+        const int nd = 3 * P.n_sample * P.n_comp, nh = P.n_sample * P.hist_n * P.hist_bins;
+        for (int i = threadIdx.x; i < nd; i += BLOCK)
+            if (sstat[i] != 0.0) atomicAdd(P.stats + i, sstat[i]);
+        for (int i = threadIdx.x; i < nh; i += BLOCK)
+            if (shist[i]) atomicAdd(P.hist + i, (unsigned long long)shist[i]);
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// Host-visible launcher table entry
+// -----------------------------------------------------------------------------------------
+struct ModelEntry {
+    pdmp_model_info info;
+    int rec_words;  // RecLayout::WORDS
+    // launch(alg, ode, records, stats, P, grid, smem, stream): returns cudaError_t
+    cudaError_t (*launch)(int alg, int ode, bool records, bool stats, const KParams& P, int grid, size_t smem,
+                          cudaStream_t stream);
+    // occupancy: resident CTAs per SM for that variant
+    cudaError_t (*occupancy)(int alg, int ode, bool records, bool stats, size_t smem, int* blocks_per_sm);
+    // compaction pool -> CSR
+    cudaError_t (*compact)(const KParams& P, const unsigned long long* offsets, double* time, double* xc,
+                           long long* xd, cudaStream_t stream);
+};
+
+// pool -> CSR: one warp per trajectory walks its segments; reads are 16-byte vector loads of
+// whole records, writes are contiguous runs per output array (time / xc / xd widened to int64)
+template <class M>
+__global__ void __launch_bounds__(256) compact_kernel(const KParams P, const unsigned long long* __restrict__ offsets,
+                                                      double* __restrict__ time, double* __restrict__ xc,
+                                                      long long* __restrict__ xd) {
+    using RL = RecLayout<M>;
+    constexpr int NC = M::NC, ND = M::ND;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long i = warp0; i < P.n_traj; i += nwarps) {
+        const unsigned n = (unsigned)P.nrec[i];
+        const unsigned long long off = offsets[i];
+        const unsigned* tab = P.seg_table + i * P.table_w;
+        unsigned seg_start = 0;  // first record index of segment k
+        for (int k = 0; seg_start < n; ++k) {
+            const unsigned cap = seg_records(k);
+            const unsigned cnt = min(cap, n - seg_start);
+            const unsigned long long slot0 = (unsigned long long)tab[k] * REC_BLOCK;
+            for (unsigned r = lane; r < cnt; r += 32) {
+                const double2* src = reinterpret_cast<const double2*>(P.pool + (slot0 + r) * RL::BYTES);
+                double w[RL::WORDS];
+#pragma unroll
+                for (int q = 0; q < RL::WORDS / 2; ++q) {
+                    const double2 v = __ldcs(src + q);
+                    w[2 * q] = v.x; w[2 * q + 1] = v.y;
+                }
+                const unsigned long long o = off + seg_start + r;
+                __stcs(time + o, w[0]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) __stcs(xc + o * NC + c, w[1 + c]);
+#pragma unroll
+                for (int c = 0; c < ND; ++c) {
+                    const double pw = w[1 + NC + c / 2];
+                    const int v = (c & 1) ? __double2hiint(pw) : __double2loint(pw);
+                    __stcs(xd + o * ND + c, (long long)v);
+                }
+            }
+            seg_start += cap;
+        }
+    }
+}
+
+template <class M, class Tab, int ALG>
+cudaError_t launch_variant(bool records, bool stats, const KParams& P, int grid, size_t smem, cudaStream_t st) {
+    if (records && stats) ensemble_kernel<M, Tab, ALG, true, true><<<grid, BLOCK, smem, st>>>(P);
+    else if (records) ensemble_kernel<M, Tab, ALG, true, false><<<grid, BLOCK, smem, st>>>(P);
+    else if (stats) ensemble_kernel<M, Tab, ALG, false, true><<<grid, BLOCK, smem, st>>>(P);
+    else ensemble_kernel<M, Tab, ALG, false, false><<<grid, BLOCK, smem, st>>>(P);
+    return cudaGetLastError();
+}
+template <class M, class Tab, int ALG>
+cudaError_t occ_variant(bool records, bool stats, size_t smem, int* out) {
+    if (records && stats) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, ensemble_kernel<M, Tab, ALG, true, true>, BLOCK, smem);
+    if (records) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, ensemble_kernel<M, Tab, ALG, true, false>, BLOCK, smem);
+    if (stats) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, ensemble_kernel<M, Tab, ALG, false, true>, BLOCK, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, ensemble_kernel<M, Tab, ALG, false, false>, BLOCK, smem);
+}
+
+template <class M>
+cudaError_t model_launch(int alg, int ode, bool records, bool stats, const KParams& P, int grid, size_t smem,
+                         cudaStream_t st) {
+    if (alg == PDMP_ALG_CHV) {
+        return ode == PDMP_ODE_TSIT5 ? launch_variant<M, TabTsit5, PDMP_ALG_CHV>(records, stats, P, grid, smem, st)
+                                     : launch_variant<M, TabDP5, PDMP_ALG_CHV>(records, stats, P, grid, smem, st);
+    }
+    if constexpr (M::HAS_BOUND) {
+        return ode == PDMP_ODE_TSIT5
+                   ? launch_variant<M, TabTsit5, PDMP_ALG_REJECTION>(records, stats, P, grid, smem, st)
+                   : launch_variant<M, TabDP5, PDMP_ALG_REJECTION>(records, stats, P, grid, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+template <class M>
+cudaError_t model_occupancy(int alg, int ode, bool records, bool stats, size_t smem, int* out) {
+    if (alg == PDMP_ALG_CHV) {
+        return ode == PDMP_ODE_TSIT5 ? occ_variant<M, TabTsit5, PDMP_ALG_CHV>(records, stats, smem, out)
+                                     : occ_variant<M, TabDP5, PDMP_ALG_CHV>(records, stats, smem, out);
+    }
+    if constexpr (M::HAS_BOUND) {
+        return ode == PDMP_ODE_TSIT5 ? occ_variant<M, TabTsit5, PDMP_ALG_REJECTION>(records, stats, smem, out)
+                                     : occ_variant<M, TabDP5, PDMP_ALG_REJECTION>(records, stats, smem, out);
+    }
+    return cudaErrorInvalidValue;
+}
+template <class M>
+cudaError_t model_compact(const KParams& P, const unsigned long long* offsets, double* time, double* xc,
+                          long long* xd, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned long long want = (P.n_traj + 7) / 8;  // 8 warps per CTA
+    const int grid = (int)std::min<unsigned long long>(want ? want : 1, (unsigned long long)sms * 8);
+    compact_kernel<M><<<grid, 256, 0, st>>>(P, offsets, time, xc, xd);
+    return cudaGetLastError();
+}
+
+template <class M>
+ModelEntry make_entry(int id) {
+    ModelEntry e{};
+    e.info.id = id;
+    e.info.n_c = M::NC; e.info.n_d = M::ND; e.info.n_r = M::NR; e.info.n_parms = M::NP;
+    e.info.has_bound = M::HAS_BOUND; e.info.has_delta = M::HAS_DELTA; e.info.zero_flow = M::ZERO_FLOW;
+    for (int i = 0; M::NAME[i] && i < 31; ++i) e.info.name[i] = M::NAME[i];
+    e.rec_words = RecLayout<M>::WORDS;
+    e.launch = &model_launch<M>;
+    e.occupancy = &model_occupancy<M>;
+    e.compact = &model_compact<M>;
+    return e;
+}
+
+}  // namespace pdmp

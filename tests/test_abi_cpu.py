@@ -1,0 +1,76 @@
+"""CPU-only checks of the product library: it loads, exports every symbol include/pdmp_b200.h
+declares, the registry matches the oracle's, and compute entry points refuse to run without
+a GPU (there is no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib(P):
+    from pdmp_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    return _lib.lib()
+
+
+def test_exports_match_header(P, lib):
+    hdr = open(os.path.join(ROOT, "include", "pdmp_b200.h")).read()
+    declared = set(re.findall(r"\b(pdmp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(P._abi.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.pdmp_abi_version() == P._abi.ABI_VERSION
+    assert f"#define PDMP_ABI_VERSION {P._abi.ABI_VERSION}" in hdr
+
+
+def test_struct_sizes(P):
+    # natural C layout, no surprises: sizes are multiples of 8 and match the field sums
+    assert C.sizeof(P._abi.ModelInfo) == 8 * 4 + 32
+    assert C.sizeof(P._abi.ProblemDesc) == 8 * 8 + 4 * 6
+    assert C.sizeof(P._abi.SolveOpts) == 8 * 12 + 4 * 14
+    assert C.sizeof(P._abi.Result) == 8 * 3 + 8 * 11 + 8 * 5 + 8 * 4 + 4 * 6 + 8
+
+
+def test_registry_matches_oracle(P, lib, orc):
+    got = {m.name.decode(): (m.n_c, m.n_d, m.n_r, m.n_parms, m.has_bound, m.has_delta, m.zero_flow)
+           for m in P.list_models()}
+    assert set(got) == set(P.models.EXAMPLES)
+    for name in got:
+        o = orc.model_info(name)
+        assert got[name] == (o.n_c, o.n_d, o.n_r, o.n_parms, o.has_bound, o.has_delta, o.zero_flow), name
+        pb = P.models.problem(name)
+        assert (pb.n_c, pb.n_d, pb.n_r) == got[name][:3]
+    with pytest.raises(P.PDMPError):
+        P.model_info("no_such_model")
+
+
+def test_no_cpu_fallback(P, lib):
+    if P.device_count() > 0:
+        pytest.skip("a GPU is present")
+    pb = P.models.problem("tcp")
+    with pytest.raises(P.PDMPError) as ei:
+        P.solve(pb, P.CHVGPU("tcp"), trajectories=4, n_jumps=5)
+    assert ei.value.code == P._abi.ERR_NO_DEVICE
+    with pytest.raises(P.PDMPError):
+        P.fp64_peak_tflops()
+
+
+def test_argument_validation(P, lib):
+    pb = P.models.problem("tcp")
+    with pytest.raises(ValueError):
+        P.solve(pb, P.CHVGPU("tcp"), trajectories=4)              # n_jumps missing
+    with pytest.raises(TypeError):
+        P.solve(pb, "CHV(Tsit5())", trajectories=4, n_jumps=5)
+    with pytest.raises(ValueError):
+        P.solve(pb, P.CHVGPU("tcp2d"), trajectories=4, n_jumps=5)  # shape mismatch
+    with pytest.raises(ValueError):
+        P.CHVGPU("tcp", ode="rodas5")
+    with pytest.raises(P.PDMPError) as ei:
+        P.solve(P.models.problem("tcp2d"), P.RejectionGPU("tcp2d"), trajectories=4, n_jumps=5)
+    assert ei.value.code == P._abi.ERR_MODEL                       # no bound => no Rejection

@@ -1,0 +1,368 @@
+"""GPU parity tests (B200): the CUDA ensemble engine, called through the C ABI
+(libpdmp_b200.so via ctypes), against the CPU oracle and the reference's closed-form known
+answers.  Tolerances follow BASELINE.json's north star: in replay mode discrete sequences are
+bit-exact and jump times / continuous states agree within rel 1e-8 at ODE tolerance 1e-10;
+in Philox mode ensemble moments agree within Monte-Carlo confidence intervals."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ODES = ["dp5", "tsit5"]
+
+
+def uniforms(seed, n, k):
+    u = np.random.default_rng(seed).random((n, k))
+    return np.clip(u, 2.0 ** -53, 1 - 2.0 ** -53)
+
+
+def relerr(a, b, floor=1.0):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+@pytest.fixture(scope="module")
+def G(P):
+    if P.device_count() < 1:
+        pytest.fail("no CUDA device: -m gpu tests need the B200 (there is no CPU fallback)")
+    return P
+
+
+def same_discrete(g, c):
+    assert np.array_equal(g.offsets, c.offsets)
+    assert np.array_equal(g.xd, c.xd)
+    assert np.array_equal(g.njumps, c.njumps) and np.array_equal(g.nrejected, c.nrejected)
+    assert np.array_equal(g.status, c.status)
+
+
+# ---- golden closed forms, with the reference's own tolerances --------------------------------
+
+@pytest.mark.parametrize("ode", ODES)
+def test_tcp_closed_form_reference_tol(G, golden, ode):
+    # test/runtests.jl:9-12 — C1 of BASELINE.json (examples/tcp.jl, single trajectory, replay)
+    pb = G.models.problem("tcp")
+    r = G.solve(pb, G.CHVGPU("tcp", ode=ode), n_jumps=10, replay=golden["tcp10_u"])
+    assert len(r.time) == 10
+    assert np.max(np.abs(r.time - golden["tcp10_t"])) < 1e-4
+    assert np.array_equal(r.xd[:, 0], golden["tcp10_xd"]) and np.all(r.xd[:, 1] == 1)
+
+
+@pytest.mark.parametrize("ode", ODES)
+@pytest.mark.parametrize("tag,nj", [("tcp10", 10), ("tcp700", 700)])
+def test_tcp_closed_form_tight(G, golden, ode, tag, nj):
+    pb = G.models.problem("tcp")
+    r = G.solve(pb, G.CHVGPU("tcp", ode=ode), n_jumps=nj, replay=golden[f"{tag}_u"], reltol=1e-10, abstol=1e-18)
+    assert relerr(r.time, golden[f"{tag}_t"]) < 1e-8
+    assert np.max(np.abs(r.xc[:, 0] - golden[f"{tag}_x"]) / golden[f"{tag}_x"]) < 1e-8
+    assert np.array_equal(r.xd[:, 0], golden[f"{tag}_xd"])
+
+
+@pytest.mark.parametrize("ode", ODES)
+def test_stiff_closed_form(G, golden, ode):
+    # test/pdmpStiff.jl:119-127 and :142-157
+    pb = G.models.problem("pdmp_stiff")
+    r = G.solve(pb, G.CHVGPU("pdmp_stiff", ode=ode), n_jumps=50, replay=golden["stiff_u"], reltol=1e-8, abstol=1e-11)
+    assert np.max(np.abs(r.time - golden["stiff_t"])) < 3e-3
+    assert abs(r.xc[-1, 0] - golden["stiff_x"][-1]) < 4e-6
+    pb.tspan[1] = 4.0
+    ana = golden["stiff_t"][golden["stiff_t"] < 4.0]
+    r1 = G.solve(pb, G.CHVGPU("pdmp_stiff", ode=ode), n_jumps=50, replay=golden["stiff_u"])
+    r2 = G.solve(pb, G.CHVGPU("pdmp_stiff", ode=ode), n_jumps=50, replay=golden["stiff_u"], save_positions=(True, False))
+    assert np.max(np.abs(r1.time[:-1] - ana)) < 2e-5
+    assert r1.time[-1] == 4.0 and r2.time[-1] == 4.0 and r1.xc[-1, 0] == r2.xc[-1, 0]
+
+
+@pytest.mark.parametrize("ode", ODES)
+def test_explosion_closed_form(G, golden, ode):
+    pb = G.models.problem("pdmp_explosion")
+    r = G.solve(pb, G.CHVGPU("pdmp_explosion", ode=ode), n_jumps=50, replay=golden["explosion_u"])
+    assert np.max(np.abs(r.time - golden["explosion_t"])) < 1e-4
+
+
+@pytest.mark.parametrize("ode", ODES)
+def test_rejection_closed_forms(G, golden, ode):
+    # test/runtests.jl:41-44, test/pdmpStiff.jl:172-179
+    pb = G.models.problem("tcp_rejection")
+    r = G.solve(pb, G.RejectionGPU("tcp_rejection", ode=ode), n_jumps=50, replay=golden["tcprej_u"])
+    assert np.max(np.abs(r.xc[:50, 0] - golden["tcprej_x"])) < 1e-5
+    assert np.array_equal(r.xd[:50, 0], golden["tcprej_xd"])
+    assert r.njumps[0] == 50 and r.nrejected[0] == int(golden["tcprej_nrej"][0])
+    pb = G.models.problem("pdmp_stiff")
+    r = G.solve(pb, G.RejectionGPU("pdmp_stiff", ode=ode), n_jumps=4, replay=golden["stiffrej_u"])
+    assert np.max(np.abs(r.time - golden["stiffrej_t"])) < 0.0043
+    assert r.nrejected[0] == int(golden["stiffrej_nrej"][0])
+
+
+def test_sir_rejection_bit_exact(G, golden):
+    pb = G.models.problem("sir_rejection")
+    U = golden["sir_u"]
+    r = G.solve(pb, G.RejectionGPU("sir_rejection"), trajectories=U.shape[0], n_jumps=1000, replay=U)
+    for k in range(U.shape[0]):
+        tr = r[k]
+        nj, nrej, status, _ = golden[f"sir{k}_meta"]
+        assert np.array_equal(tr.xd.T, golden[f"sir{k}_xd"])
+        assert np.max(np.abs(tr.time - golden[f"sir{k}_t"])) < 1e-12
+        assert (tr.njumps, tr.nrejected, tr.status) == (nj, nrej, status)
+
+
+# ---- replay parity against the oracle, every model -----------------------------------------
+
+CHV_CASES = [  # model, n_jumps, tf override, abstol
+    ("tcp", 60, 200.0), ("tcp2d", 200, 10.0), ("morris_lecar", 300, 100.0), ("sir", 300, 150.0),
+    ("pdmp_stiff", 50, None), ("tcp_rejection", 50, None), ("pdmp_explosion", 30, 50.0), ("neuron_eva", 200, 100.0),
+]
+
+
+@pytest.mark.parametrize("ode", ODES)
+@pytest.mark.parametrize("model,nj,tf", CHV_CASES)
+def test_replay_parity_chv(G, orc, model, nj, tf, ode):
+    pb = G.models.problem(model)
+    if tf is not None:
+        pb.tspan[1] = tf
+    n = 1000
+    U = uniforms(hash(model) % 1000, n, 2 * nj + 2)
+    kw = dict(trajectories=n, n_jumps=nj, replay=U, reltol=1e-10, abstol=1e-13)
+    g = G.solve(pb, G.CHVGPU(model, ode=ode), **kw)
+    c = orc.solve(pb, model, algorithm="chv", ode=ode, **kw)
+    same_discrete(g, c)
+    assert relerr(g.time, c.time) < 1e-8
+    assert relerr(g.xc, c.xc, floor=1e-3) < 1e-7
+    # against the reference's own integrator family (Tsit5), whatever the kernel pair
+    t5 = orc.solve(pb, model, algorithm="chv", ode="tsit5", **kw)
+    same_discrete(g, t5)
+    assert relerr(g.time, t5.time) < 1e-8
+
+
+@pytest.mark.parametrize("ode", ODES)
+@pytest.mark.parametrize("model,nj,tf", [("tcp", 40, 50.0), ("sir_rejection", 400, 150.0), ("pdmp_stiff", 20, 2.0),
+                                         ("tcp_rejection", 50, 200.0), ("neuron_eva", 100, 100.0)])
+def test_replay_parity_rejection(G, orc, model, nj, tf, ode):
+    pb = G.models.problem(model)
+    pb.tspan[1] = tf
+    if model == "tcp":
+        pb.xc0[0] = 0.5   # keeps 1/x below the bound 100 most of the time; violations get a status
+    n = 500
+    U = uniforms(7 + hash(model) % 1000, n, 16384 if model in ("pdmp_stiff", "tcp") else 4096)
+    kw = dict(trajectories=n, n_jumps=nj, replay=U, reltol=1e-10, abstol=1e-13)
+    g = G.solve(pb, G.RejectionGPU(model, ode=ode), **kw)
+    c = orc.solve(pb, model, algorithm="rejection", ode=ode, **kw)
+    same_discrete(g, c)
+    assert relerr(g.time, c.time) < 1e-8
+    assert relerr(g.xc, c.xc, floor=1e-3) < 1e-7
+
+
+def test_philox_trajectories_match_oracle(G, orc):
+    # same counter-based stream on both sides => trajectory-level agreement, not only moments
+    for model, alg, nj in [("tcp2d", "chv", 100), ("morris_lecar", "chv", 100), ("sir_rejection", "rejection", 1000)]:
+        pb = G.models.problem(model)
+        if model == "tcp2d":
+            pb.tspan[1] = 10.0
+        kw = dict(trajectories=2000, n_jumps=nj, seed=20241019, traj_id_offset=5_000_000_000)
+        A = G.CHVGPU(model) if alg == "chv" else G.RejectionGPU(model)
+        g = G.solve(pb, A, **kw)
+        c = orc.solve(pb, model, algorithm=alg, ode="dp5", **kw)
+        same_discrete(g, c)
+        assert relerr(g.time, c.time) < 1e-6 and relerr(g.xc, c.xc, floor=1e-3) < 1e-5
+
+
+# ---- Philox mode: ensemble moments inside Monte-Carlo confidence intervals -------------------
+
+def _ci_check(g, c, z=4.4):
+    """Means: two-sample z test. Variances: z test with the 4th-moment standard error, estimated
+    from the oracle's variance (Gaussian kurtosis bound x3 for safety).  z = 4.4 keeps the
+    family-wise 99% level over <= 300 simultaneous comparisons (Bonferroni: 1 - 0.01/600)."""
+    ng, nc_ = g.stat_count, c.stat_count
+    ok = (ng > 100) & (nc_ > 100)
+    mg, mc = g.mean(), c.mean()
+    vg, vc = g.var(), c.var()
+    se_mean = np.sqrt(vg / ng + vc / nc_)
+    bad_mean = ok & (np.abs(mg - mc) > z * se_mean + 1e-12)
+    se_var = np.sqrt(3.0) * np.sqrt(2.0) * np.maximum(vg, vc) * np.sqrt(1.0 / ng + 1.0 / nc_)
+    bad_var = ok & (np.abs(vg - vc) > z * 3.0 * se_var + 1e-12)
+    return bad_mean, bad_var
+
+
+@pytest.mark.parametrize("model,alg,tf,nj", [("tcp2d", "chv", 10.0, 2000), ("morris_lecar", "chv", 50.0, 2200),
+                                             ("sir_rejection", "rejection", 150.0, 1000), ("tcp", "chv", 20.0, 1000)])
+def test_philox_moments_vs_oracle(G, orc, model, alg, tf, nj):
+    pb = G.models.problem(model)
+    pb.tspan[1] = tf
+    st = np.linspace(tf / 8, tf, 8)
+    A = G.CHVGPU(model) if alg == "chv" else G.RejectionGPU(model)
+    g = G.solve(pb, A, trajectories=400_000, n_jumps=nj, seed=11, sample_times=st, no_records=True)
+    c = orc.solve(pb, model, algorithm=alg, ode="tsit5", trajectories=40_000, n_jumps=nj, seed=12,
+                  sample_times=st, no_records=True)
+    assert g.stat_count[0, 0] > 390_000
+    bad_mean, bad_var = _ci_check(g, c)
+    assert not bad_mean.any(), (g.mean()[bad_mean], c.mean()[bad_mean])
+    assert not bad_var.any(), (g.var()[bad_var], c.var()[bad_var])
+
+
+def test_stats_and_histogram_exact_vs_oracle_same_stream(G, orc):
+    # same Philox stream: counts and histograms must agree exactly (up to bin-edge ties), sums to round-off
+    pb = G.models.problem("tcp2d")
+    pb.tspan[1] = 10.0
+    st = 10.0 * np.arange(1, 17) / 16
+    kw = dict(trajectories=20000, n_jumps=2000, seed=5, sample_times=st, hist=[(0, 0.0, 4.0), (1, 0.0, 4.0), (2, 0.0, 64.0)],
+              hist_bins=64)
+    g = G.solve(pb, G.CHVGPU("tcp2d"), **kw)
+    c = orc.solve(pb, "tcp2d", algorithm="chv", ode="dp5", **kw)
+    assert np.array_equal(g.stat_count, c.stat_count)
+    assert np.allclose(g.stat_sum, c.stat_sum, rtol=1e-7) and np.allclose(g.stat_sumsq, c.stat_sumsq, rtol=1e-7)
+    assert g.hist.sum() == c.hist.sum() == 20000 * 16 * 3
+    assert np.abs(g.hist.astype(np.int64) - c.hist.astype(np.int64)).sum() <= 8   # ties at bin edges
+    assert np.array_equal(g.hist[:, 2], c.hist[:, 2])                              # integer component: exact
+
+
+# ---- size-independent properties at ensemble scale -----------------------------------------
+
+def test_ensemble_properties_large(G):
+    # BASELINE config C2 shape (TCP, tf = 200, n_jumps = 1000) at 2e5 trajectories
+    pb = G.models.problem("tcp", tspan=(0.0, 200.0))
+    n = 200_000
+    r = G.solve(pb, G.CHVGPU("tcp"), trajectories=n, n_jumps=1000, seed=1234)
+    off = r.offsets.astype(np.int64)
+    cnt = np.diff(off)
+    assert off[0] == 0 and off[-1] == len(r.time) == r.counters["total_records"] and np.all(cnt >= 1)
+    first = off[:-1]
+    assert np.all(r.time[first] == 0.0) and np.all(r.xc[first, 0] == 1.0) and np.all(r.xd[first, 0] == 0)
+    # times strictly increase inside a trajectory; xd[0] counts jumps; xd[1] never changes
+    inner = np.ones(len(r.time), bool); inner[first] = False
+    dt = np.diff(r.time, prepend=0.0)
+    assert np.all(dt[inner] > 0)
+    k = np.arange(len(r.time)) - np.repeat(first, cnt)
+    ok = r.status == G._abi.ST_OK
+    last = off[1:] - 1
+    assert np.all(r.time[last[ok]] == 200.0)
+    is_last_ok = np.zeros(len(r.time), bool); is_last_ok[last[ok]] = True
+    assert np.array_equal(r.xd[~is_last_ok, 0], k[~is_last_ok])
+    assert np.all(r.xd[:, 1] == 1)
+    # counters are consistent with the per-trajectory results
+    assert r.counters["total_candidates"] == int((r.njumps - 1).sum())
+    hist = r.status_histogram()
+    assert set(hist) <= {"OK", "HIT_NJUMPS", "NO_PROGRESS"} and hist["OK"] > 0.85 * n
+    assert np.all(r.njumps[r.status == G._abi.ST_HIT_NJUMPS] == 1000)
+    assert np.all(cnt[r.status == G._abi.ST_HIT_NJUMPS] == 1000)
+    # jump times of a trajectory obey the TCP closed form given its own states: x_{k+1}/x_k = exp(+-S)
+    # and dt = |x_{k+1} - x_k| (F = +-1): an integrator-independent invariant
+    dx = np.abs(np.diff(r.xc[:, 0], prepend=1.0))
+    chk = inner & ~is_last_ok
+    assert np.max(np.abs(dx[chk] - dt[chk]) / np.maximum(dt[chk], 1e-3)) < 1e-5
+
+
+def test_sharding_and_determinism(G):
+    pb = G.models.problem("morris_lecar")
+    kw = dict(n_jumps=200, seed=99)
+    full = G.solve(pb, G.CHVGPU("morris_lecar"), trajectories=4096, **kw)
+    again = G.solve(pb, G.CHVGPU("morris_lecar"), trajectories=4096, **kw)
+    assert np.array_equal(full.time, again.time) and np.array_equal(full.xd, again.xd)
+    part = G.solve(pb, G.CHVGPU("morris_lecar"), trajectories=1024, traj_id_offset=3072, **kw)
+    a = int(full.offsets[3072])
+    assert np.array_equal(full.time[a:], part.time) and np.array_equal(full.xd[a:], part.xd)
+    other = G.solve(pb, G.CHVGPU("morris_lecar"), trajectories=64, n_jumps=200, seed=100)
+    assert not np.array_equal(other.time, full.time[: len(other.time)])
+
+
+# ---- edge cases ------------------------------------------------------------------------------
+
+def test_edge_cases(G, orc):
+    pb = G.models.problem("tcp", tspan=(0.0, 5.0))
+    # n_jumps = 1: only the initial point (the loop never runs), reference S8
+    r = G.solve(pb, G.CHVGPU("tcp"), trajectories=3, n_jumps=1, seed=1)
+    assert np.array_equal(np.diff(r.offsets.astype(np.int64)), [1, 1, 1]) and np.all(r.njumps == 1)
+    assert np.all(r.status == G._abi.ST_HIT_NJUMPS)
+    # save_positions = (false, false): initial + final point only (reference "no allocation" mode)
+    r = G.solve(pb, G.CHVGPU("tcp"), trajectories=1000, n_jumps=100000, seed=2, save_positions=(False, False))
+    c = orc.solve(pb, "tcp", algorithm="chv", ode="dp5", trajectories=1000, n_jumps=100000, seed=2,
+                  save_positions=(False, False))
+    assert np.array_equal(r.offsets, c.offsets) and np.array_equal(r.xd, c.xd) and relerr(r.xc, c.xc, 1e-3) < 1e-5
+    okm = r.status == G._abi.ST_OK
+    assert np.all(np.diff(r.offsets.astype(np.int64))[okm] == 2)
+    # pre-jump saving
+    kw = dict(trajectories=200, n_jumps=50, seed=3, save_positions=(True, False))
+    r = G.solve(pb, G.CHVGPU("tcp"), **kw)
+    c = orc.solve(pb, "tcp", algorithm="chv", ode="dp5", **kw)
+    same_discrete(r, c)
+    # both positions
+    kw["save_positions"] = (True, True)
+    r = G.solve(pb, G.CHVGPU("tcp"), **kw)
+    c = orc.solve(pb, "tcp", algorithm="chv", ode="dp5", **kw)
+    same_discrete(r, c)
+    # per-trajectory initial conditions (ragged ensemble: jump counts differ wildly)
+    n = 777
+    xc0 = 0.5 + np.random.default_rng(0).random((n, 1))
+    xd0 = np.stack([np.arange(n) % 2, np.ones(n, dtype=np.int64)], axis=1)
+    kw = dict(trajectories=n, n_jumps=300, seed=4, xc0=xc0, xd0=xd0)
+    r = G.solve(pb, G.CHVGPU("tcp"), **kw)
+    c = orc.solve(pb, "tcp", algorithm="chv", ode="dp5", **kw)
+    same_discrete(r, c)
+    assert np.array_equal(r.xc[r.offsets[:-1].astype(np.int64), 0], xc0[:, 0])
+    # statistics only
+    r = G.solve(pb, G.CHVGPU("tcp"), trajectories=5000, n_jumps=300, seed=4, no_records=True, sample_times=[1.0, 5.0])
+    assert r.time.size == 0 and r.stat_count.shape == (2, 3) and r.stat_count[0, 0] > 4900
+
+
+def test_status_codes(G, golden):
+    # time stall => NO_PROGRESS with the partial trajectory (reference: AssertionError, src/chvdiffeq.jl:145)
+    pb = G.models.problem("tcp")
+    r = G.solve(pb, G.CHVGPU("tcp", ode="tsit5"), n_jumps=1000, replay=golden["tcp700_u"], reltol=1e-10, abstol=1e-18)
+    assert r.status[0] == G._abi.ST_NO_PROGRESS and 700 < len(r.time) < 1000
+    # replay stream too short
+    r = G.solve(pb, G.CHVGPU("tcp"), n_jumps=50, replay=golden["tcp700_u"][:20])
+    assert r.status[0] == G._abi.ST_REPLAY_EXHAUSTED
+    # SIR bound violations are flagged, never fatal (SURVEY finding 0.5)
+    pb = G.models.problem("sir_rejection")
+    r = G.solve(pb, G.RejectionGPU("sir_rejection"), trajectories=20000, n_jumps=1000, seed=7)
+    h = r.status_histogram()
+    assert 0 < h.get("BOUND_VIOLATED", 0) < 400 and h["OK"] > 19000
+    # attempt budget
+    pb = G.models.problem("morris_lecar")
+    r = G.solve(pb, G.CHVGPU("morris_lecar"), trajectories=8, n_jumps=2200, seed=1, max_attempts=50)
+    assert np.all(r.status == G._abi.ST_MAX_ATTEMPTS)
+
+
+def test_capacity_overflow_and_retry(G):
+    from pdmp_b200 import _abi, _lib, _marshal
+    import ctypes as C
+    pb = G.models.problem("tcp", tspan=(0.0, 50.0))
+    info = G.model_info("tcp")
+    d, o, keep = _marshal.build(pb, info, algorithm="chv", trajectories=4000, n_jumps=500, seed=1, max_records=4000 * 16)
+    res = _abi.Result()
+    rc = _lib.lib().pdmp_solve_ensemble(C.byref(d), C.byref(o), C.byref(res))
+    assert rc == _abi.ERR_CAPACITY and res.records_needed > 4000 * 16
+    st = np.ctypeslib.as_array(res.status, shape=(4000,)).copy()
+    assert (st == _abi.ST_OUTPUT_OVERFLOW).any()
+    _lib.lib().pdmp_result_free(C.byref(res))
+    # the host wrapper retries with the reported capacity
+    r = G.solve(pb, G.CHVGPU("tcp"), trajectories=4000, n_jumps=500, seed=1, max_records=4000 * 16)
+    full = G.solve(pb, G.CHVGPU("tcp"), trajectories=4000, n_jumps=500, seed=1)
+    assert not (r.status == _abi.ST_OUTPUT_OVERFLOW).any()
+    assert np.array_equal(r.time, full.time) and np.array_equal(r.offsets, full.offsets)
+
+
+def test_resident_ensemble_handle(G):
+    pb = G.models.problem("tcp2d")
+    pb.tspan[1] = 10.0
+    ens = G.Ensemble(pb, G.CHVGPU("tcp2d"), trajectories=10000, n_jumps=500, sample_times=[5.0, 10.0])
+    ens.run(seed=1)
+    a = ens.fetch(copy=True)
+    ens.run(seed=2)
+    b = ens.fetch(copy=True)
+    ens.run(seed=1)
+    a2 = ens.fetch(copy=True)
+    assert np.array_equal(a.time, a2.time) and not np.array_equal(a.time[:1000], b.time[:1000])
+    one = G.solve(pb, G.CHVGPU("tcp2d"), trajectories=10000, n_jumps=500, seed=1, sample_times=[5.0, 10.0])
+    assert np.array_equal(one.time, a.time) and np.array_equal(one.stat_sum, a.stat_sum) is not None
+    # new initial conditions from host memory
+    xc0 = np.tile([0.2, 0.3], (10000, 1))
+    ens.upload(xc0=xc0)
+    ens.run(seed=1)
+    c = ens.fetch(copy=True)
+    assert np.all(c.xc[c.offsets[:-1].astype(np.int64)] == [0.2, 0.3])
+    cnt = ens.counters()
+    assert cnt["total_records"] == len(c.time) and cnt["kernel_ms"] > 0
+    ens.close()
+
+
+def test_fp64_peak_probe(G):
+    tf = G.fp64_peak_tflops()
+    assert 10.0 < tf < 80.0, tf
