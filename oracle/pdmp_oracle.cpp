@@ -337,7 +337,17 @@ struct Integrator {
                 e2 += r * r;
             }
             const double EEst = std::sqrt(e2 / D);
-            if (!std::isfinite(EEst)) { *fail_status = PDMP_ST_NAN; return false; }
+            if (!std::isfinite(EEst)) {
+                // a trial step that left the domain of F/R (overflow, 1/0): OrdinaryDiffEq rejects
+                // an infinite estimate with the maximal shrink 1/qmin; only a non-finite ACCEPTED
+                // state (or a step that no longer advances t) is fatal
+                bool state_ok = true;
+                for (int i = 0; i < D; ++i) state_ok = state_ok && std::isfinite(u[i]) && std::isfinite(k[0][i]);
+                if (!state_ok || !(t + 0.2 * h > t)) { *fail_status = PDMP_ST_NAN; return false; }
+                ++rejects;
+                dt = 0.2 * h;
+                continue;
+            }
             double q11 = 0, q;
             if (EEst == 0.0) q = 1.0 / QMAX;
             else {

@@ -30,6 +30,8 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
     if n_jumps is None or not np.isfinite(n_jumps):
         raise ValueError("n_jumps must be given and finite for an ensemble solve (the reference "
                          "default Inf64 has no meaning with heavy-tailed jump counts)")
+    if not (problem.tspan[0] < problem.tspan[1]):
+        raise ValueError("tspan must satisfy t0 < tf")
     if problem.n_c != info.n_c or problem.n_d != info.n_d or problem.n_r != info.n_r:
         raise ValueError(
             f"problem shape (n_c={problem.n_c}, n_d={problem.n_d}, n_r={problem.n_r}) does not match "

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -65,8 +66,11 @@ struct Pinned {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        cudaError_t e = cudaHostAlloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault);
-        if (e == cudaSuccess) cap = n;
+        // pinning is slow (~GB/s): grow with headroom so that runs whose record count drifts by a
+        // few percent (different seed) do not re-pin
+        const size_t want = std::max<size_t>(n + n / 8 + 1024, 1);
+        cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     ~Pinned() { if (p) cudaFreeHost(p); }
@@ -151,6 +155,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     const ModelEntry& m = registry()[d->model_id];
     const int NC = m.info.n_c, ND = m.info.n_d, NR = m.info.n_r;
     if (o->n_jumps < 1) return fail(PDMP_ERR_INVALID, "n_jumps must be >= 1 and finite");
+    if (!(d->t0 < d->tf)) return fail(PDMP_ERR_INVALID, "tspan must satisfy t0 < tf");
     if (!(o->reltol > 0) || !(o->abstol > 0)) return fail(PDMP_ERR_INVALID, "reltol and abstol must be > 0");
     if (d->n_parms < m.info.n_parms || d->n_parms > MAXP)
         return fail(PDMP_ERR_MODEL, std::string("model '") + m.info.name + "' reads " +
@@ -190,6 +195,12 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     P.max_attempts = o->max_attempts > 0 ? o->max_attempts : 1000000ll;
     P.save_pre = o->save_pre; P.save_post = o->save_post; P.tstop_policy = o->tstop_policy;
     P.rng_mode = o->rng_mode; P.seed = o->seed; P.replay_stride = o->replay_stride;
+    {   // phase-scheduler thresholds (tunable for experiments)
+        const char* ej = std::getenv("PDMP_JUMP_THRESH");
+        const char* er = std::getenv("PDMP_REFILL_THRESH");
+        P.jump_thresh = ej ? std::max(1, std::atoi(ej)) : 12;
+        P.refill_thresh = er ? std::max(1, std::atoi(er)) : 2;
+    }
     P.n_sample = o->n_sample_times; P.n_comp = NC + ND; P.hist_n = o->hist_n; P.hist_bins = o->hist_n ? o->hist_bins : 0;
     e->records = !o->no_records;
     e->stats = o->n_sample_times > 0;

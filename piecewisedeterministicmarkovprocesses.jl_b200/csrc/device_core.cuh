@@ -36,6 +36,21 @@ PDMP_DEV double rcp_fast(double x) {
 #endif
 }
 
+// same, for arguments known to be positive and in the normal range (error weights
+// abstol + |u| reltol): no fallback branch
+PDMP_DEV double rcp_pos(double x) {
+#ifdef PDMP_EXACT_DIV
+    return 1.0 / x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  counter = (gid_lo, gid_hi, block, 0),
 // key = (seed_lo, seed_hi).  One call yields two 52-bit uniforms in (0,1): exactly one
@@ -81,8 +96,36 @@ struct DrawStream {
 // Tableaus.  a(s, j): coefficient of k_{j+1} in stage s+2 (s = 0..5; s = 5 is the b row),
 // bt(j): b - bhat.  constexpr functions so that fully unrolled loops fold the zeros away.
 // ---------------------------------------------------------------------------------------
+// Coefficient VALUES are read from __constant__ memory (they become c[bank][offset] operands of
+// DFMA/DMUL: no instruction is spent materialising 64-bit immediates); the constexpr copies
+// only drive compile-time structure (which coefficients are zero).
+static __constant__ double c_dp5_a[6][6] = {
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+static __constant__ double c_dp5_bt[7] = {71.0 / 57600, 0.0, -71.0 / 16695, 71.0 / 1920, -17253.0 / 339200,
+                                          22.0 / 525, -1.0 / 40};
+static __constant__ double c_dp5_c[7] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
+static __constant__ double c_ts5_a[6][6] = {
+    {0.161, 0, 0, 0, 0, 0},
+    {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+static __constant__ double c_ts5_bt[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995,
+                                          -0.1447110071732629,     0.5823571654525552,     -0.45808210592918697,
+                                          1.0 / 66.0};
+static __constant__ double c_ts5_c[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+
 struct TabDP5 {
     static constexpr int ID = 0;
+    PDMP_DEV static double A(int s, int j) { return c_dp5_a[s][j]; }
+    PDMP_DEV static double BT(int j) { return c_dp5_bt[j]; }
+    PDMP_DEV static double C(int i) { return c_dp5_c[i]; }
     __host__ __device__ static constexpr double c(int i) {
         constexpr double C[7] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
         return C[i];
@@ -106,6 +149,9 @@ struct TabDP5 {
 
 struct TabTsit5 {
     static constexpr int ID = 1;
+    PDMP_DEV static double A(int s, int j) { return c_ts5_a[s][j]; }
+    PDMP_DEV static double BT(int j) { return c_ts5_bt[j]; }
+    PDMP_DEV static double C(int i) { return c_ts5_c[i]; }
     __host__ __device__ static constexpr double c(int i) {
         constexpr double C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
         return C[i];
@@ -145,27 +191,27 @@ PDMP_DEV double rk_attempt(RHS&& f, const double (&u)[D], const double (&k1)[D],
         double us[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-            double acc = Tab::a(s - 1, 0) * k[0][i];
+            double acc = Tab::A(s - 1, 0) * k[0][i];
 #pragma unroll
             for (int j = 1; j < s; ++j)
-                if (Tab::a(s - 1, j) != 0.0) acc = fma(Tab::a(s - 1, j), k[j][i], acc);
+                if (Tab::a(s - 1, j) != 0.0) acc = fma(Tab::A(s - 1, j), k[j][i], acc);
             us[i] = fma(h, acc, u[i]);
         }
         if (s == 6) {
 #pragma unroll
             for (int i = 0; i < D; ++i) unew[i] = us[i];
         }
-        f(us, k[s], t + Tab::c(s) * h);
+        f(us, k[s], fma(Tab::C(s), h, t));
     }
     double e2 = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-        double acc = Tab::bt(0) * k[0][i];
+        double acc = Tab::BT(0) * k[0][i];
 #pragma unroll
         for (int j = 1; j < 7; ++j)
-            if (Tab::bt(j) != 0.0) acc = fma(Tab::bt(j), k[j][i], acc);
+            if (Tab::bt(j) != 0.0) acc = fma(Tab::BT(j), k[j][i], acc);
         const double sc = fma(fmax(fabs(u[i]), fabs(unew[i])), reltol, abstol);
-        const double r = (h * acc) * rcp_fast(sc);
+        const double r = (h * acc) * rcp_pos(sc);
         e2 = fma(r, r, e2);
         k7[i] = k[6][i];
     }

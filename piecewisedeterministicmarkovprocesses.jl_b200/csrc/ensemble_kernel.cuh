@@ -39,6 +39,7 @@ struct KParams {
     double reltol, abstol;
     long long n_jumps, max_attempts;
     int save_pre, save_post, tstop_policy, rng_mode;
+    int jump_thresh, refill_thresh;  // phase scheduler: lanes that must wait before JUMP / REFILL run
     unsigned long long seed;
     const double* replay_u;
     unsigned long long replay_stride;
@@ -212,9 +213,17 @@ struct Traj {
             double xn[NC], f7[NC];
             const double e2 = rk_attempt<Tab, NC>(rhs, xs, f1, ts, step, xn, f7, P.reltol, P.abstol);
             if (++aux_attempts > budget) { fail = PDMP_ST_MAX_ATTEMPTS; return false; }
-            if (!(e2 == e2) || isinf(e2)) { fail = PDMP_ST_NAN; return false; }
             const bool accept = e2 <= (double)NC;
-            const double fac = c2.step(e2 * (1.0 / NC), accept);
+            double fac;
+            if (!(e2 == e2) || isinf(e2)) {
+                bool ok = true;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) ok = ok && isfinite(xs[i]) && isfinite(f1[i]);
+                if (!ok || !(ts + 0.2 * step > ts)) { fail = PDMP_ST_NAN; return false; }
+                fac = 0.2;
+            } else {
+                fac = c2.step(e2 * (1.0 / NC), accept);
+            }
             if (accept) {
 #pragma unroll
                 for (int i = 0; i < NC; ++i) { xs[i] = xn[i]; f1[i] = f7[i]; }
@@ -292,7 +301,8 @@ struct Traj {
         for (int i = 0; i < D; ++i) { const double a = (f1[i] - k1[i]) / sk[i]; d2 = fma(a, a, d2); }
         d2 = sqrt(d2 * (1.0 / D)) / dt0;
         const double dm = fmax(d1, d2);
-        const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) / 5.0);
+        // 10^(-(2 + log10 dm)/5) = (100 dm)^(-1/5), evaluated in FP32 (it only seeds the controller)
+        const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : (double)exp2f(-0.2f * __log2f((float)(100.0 * dm)));
         h = fmin(fmin(100.0 * dt0, dt1), 1e9);
     }
 
@@ -406,10 +416,22 @@ struct Traj {
     }
 };
 
+// resident CTAs per SM the kernel is compiled for: small models fit 6 x 128 threads in the
+// register file (<= 80 registers), the larger ones 4 (<= 128 registers)
+template <class M, int ALG>
+struct MinBlocks {
+    static constexpr int D = (ALG == PDMP_ALG_CHV) ? M::NC + 1 : M::NC;
+    static constexpr int value = (D <= 2 && M::NR <= 2 && M::ND <= 2) ? 6 : 4;
+};
+
+// lane states of the phase scheduler
+enum { LANE_DEAD = 0, LANE_RUN = 1, LANE_WAIT = 2, LANE_EXHAUSTED = 3 };
+
 template <class M, class Tab, int ALG, bool RECORDS, bool STATS>
-__global__ void __launch_bounds__(BLOCK) ensemble_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kernel(const __grid_constant__ KParams P) {
     using T = Traj<M, Tab, ALG, RECORDS, STATS>;
     constexpr int D = T::D;
+    constexpr bool NO_FLOW = (ALG == PDMP_ALG_REJECTION && M::ZERO_FLOW);
     extern __shared__ double smem[];
     double* sstat = smem;
     unsigned* shist = reinterpret_cast<unsigned*>(smem + 3 * P.n_sample * P.n_comp);
@@ -421,41 +443,64 @@ __global__ void __launch_bounds__(BLOCK) ensemble_kernel(const __grid_constant__
     }
 
     T tr;
-    bool alive = false, exhausted = false;
+    int st = LANE_DEAD;
     const unsigned lane = threadIdx.x & 31u;
     unsigned c_attempts = 0, c_rejects = 0, c_aux = 0, c_jumps = 0, c_cands = 0;
     unsigned long long g_attempts = 0;  // spill-over of the 32-bit attempt counter
     const unsigned budget = (unsigned)min((long long)0x7fffffff, P.max_attempts);
 
+    // Phase scheduler.  Every iteration the warp does ONE of three things, chosen warp-uniformly:
+    //   RK     one adaptive step attempt for every RUN lane (the arithmetic-heavy, converged part)
+    //   JUMP   the threshold section for every WAIT lane — deferred until enough lanes wait, so
+    //          that its ~300 instructions are issued for many lanes at once instead of ~5
+    //   REFILL trajectories for DEAD lanes from the global cursor (warp-aggregated atomic)
     for (;;) {
-        // ---- refill finished lanes from the global cursor (warp-aggregated) ----
-        const unsigned need = __ballot_sync(0xffffffffu, !alive && !exhausted);
-        if (need) {
+        const unsigned m_run = __ballot_sync(0xffffffffu, st == LANE_RUN);
+        const unsigned m_wait = __ballot_sync(0xffffffffu, st == LANE_WAIT);
+        const unsigned m_dead = __ballot_sync(0xffffffffu, st == LANE_DEAD);
+        if (!(m_run | m_wait | m_dead)) break;
+        const int n_run = __popc(m_run), n_wait = __popc(m_wait), n_dead = __popc(m_dead);
+
+        if (n_dead && (n_dead >= P.refill_thresh || n_run == 0)) {
+            // ---- REFILL ----
             unsigned long long base = 0;
-            const int leader = __ffs(need) - 1;
-            if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)__popc(need));
+            const int leader = __ffs(m_dead) - 1;
+            if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)n_dead);
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (!alive && !exhausted) {
-                const unsigned long long idx = base + __popc(need & ((1u << lane) - 1u));
+            if (st == LANE_DEAD) {
+                const unsigned long long idx = base + __popc(m_dead & ((1u << lane) - 1u));
                 if (idx < P.n_traj) {
                     bool ex = false;
                     tr.init(P, (unsigned)idx, ex);
-                    alive = true;
+                    // while (t < tf) && (njumps < n_jumps): may be false before the first step
+                    if (!(tr.simnj < P.n_jumps)) tr.finish(P, PDMP_ST_HIT_NJUMPS);
+                    else if (ex) tr.finish(P, PDMP_ST_REPLAY_EXHAUSTED);
+                    else if (NO_FLOW) { tr.s = tr.tstop; st = LANE_WAIT; }
+                    else st = LANE_RUN;
                 } else {
-                    exhausted = true;
+                    st = LANE_EXHAUSTED;
                 }
             }
+            continue;
         }
-        if (__all_sync(0xffffffffu, !alive)) break;
-        if (!alive) continue;
 
-        // ---- one adaptive RK attempt, clipped at the threshold (tstops) ----
-        bool hit = false;
-        if (ALG == PDMP_ALG_REJECTION && M::ZERO_FLOW) {
-            // F = F_dummy: the flow is the identity, go straight to the candidate time
-            tr.s = tr.tstop;
-            hit = true;
-        } else {
+        const int n_live = n_run + n_wait;
+        if (n_wait && (n_run == 0 || n_wait >= min(P.jump_thresh, (n_live + 1) >> 1))) {
+            // ---- JUMP ----
+            if (st == LANE_WAIT) {
+                ++c_cands;
+                bool done;
+                if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, sstat, shist, c_aux, c_jumps);
+                else done = tr.rej_candidate(P, sstat, shist, c_aux, c_jumps);
+                if (done) st = LANE_DEAD;
+                else if (NO_FLOW) { tr.s = tr.tstop; }   // F = F_dummy: next candidate directly
+                else st = LANE_RUN;
+            }
+            continue;
+        }
+
+        // ---- RK: one adaptive attempt, clipped at the threshold (tstops) ----
+        if (st == LANE_RUN) {
             const double hprop = tr.h;
             double step = hprop;
             bool clipped = false;
@@ -465,33 +510,37 @@ __global__ void __launch_bounds__(BLOCK) ensemble_kernel(const __grid_constant__
             auto rhs = [&](const double* x, double* dx, double t) { tr.field(P, x, dx, t); };
             const double e2 = rk_attempt<Tab, D>(rhs, tr.y, tr.k1, tr.s, step, yn, k7, P.reltol, P.abstol);
             ++c_attempts;
-            if (!(e2 == e2) || isinf(e2)) { tr.finish(P, PDMP_ST_NAN); alive = false; continue; }
-            if (++tr.attempts > budget) { tr.finish(P, PDMP_ST_MAX_ATTEMPTS); alive = false; continue; }
             const bool accept = e2 <= (double)D;
-            const double fac = tr.pi.step(e2 * (1.0 / D), accept);
-            double hnext = step * fac;
-            if (accept) {
-#pragma unroll
-                for (int i = 0; i < D; ++i) { tr.y[i] = yn[i]; tr.k1[i] = k7[i]; }
-                double sn = tr.s + step;
-                if (clipped || fabs(sn - tr.tstop) < 100.0 * 2.220446049250313e-16 * fmax(fabs(sn), fabs(tr.tstop))) {
-                    sn = tr.tstop;
-                    hit = true;
-                }
-                tr.s = sn;
-                if (clipped && P.tstop_policy == 1) hnext = fmax(hnext, hprop);
+            double hnext;
+            if (e2 < 1.7976931348623157e308) {  // finite (false for NaN and Inf)
+                hnext = step * tr.pi.step(e2 * (1.0 / D), accept);
             } else {
-                ++c_rejects;
+                // trial step left the domain of F/R: reject with the maximal shrink (what
+                // OrdinaryDiffEq does with an infinite estimate); fatal only if the accepted
+                // state itself is non-finite or the step no longer advances s
+                bool ok = true;
+#pragma unroll
+                for (int i = 0; i < D; ++i) ok = ok && isfinite(tr.y[i]) && isfinite(tr.k1[i]);
+                hnext = 0.2 * step;
+                if (!ok || !(tr.s + hnext > tr.s)) { tr.finish(P, PDMP_ST_NAN); st = LANE_DEAD; }
             }
-            tr.h = hnext;
-        }
-        // ---- threshold reached: jump section (divergent, short) ----
-        if (hit) {
-            ++c_cands;
-            bool done;
-            if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, sstat, shist, c_aux, c_jumps);
-            else done = tr.rej_candidate(P, sstat, shist, c_aux, c_jumps);
-            if (done) alive = false;
+            if (st == LANE_RUN && ++tr.attempts > budget) { tr.finish(P, PDMP_ST_MAX_ATTEMPTS); st = LANE_DEAD; }
+            if (st == LANE_RUN) {
+                if (accept) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) { tr.y[i] = yn[i]; tr.k1[i] = k7[i]; }
+                    double sn = tr.s + step;
+                    if (clipped || fabs(sn - tr.tstop) < 100.0 * 2.220446049250313e-16 * fmax(fabs(sn), fabs(tr.tstop))) {
+                        sn = tr.tstop;
+                        st = LANE_WAIT;
+                    }
+                    tr.s = sn;
+                    if (clipped && P.tstop_policy == 1) hnext = fmax(hnext, hprop);
+                } else {
+                    ++c_rejects;
+                }
+                tr.h = hnext;
+            }
         }
         if (c_attempts > 0x40000000u) { g_attempts += c_attempts; c_attempts = 0; }
     }

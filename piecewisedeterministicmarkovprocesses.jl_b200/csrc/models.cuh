@@ -39,7 +39,8 @@ struct TcpDev {  // examples/tcp.jl:25-45
     PDMP_DEV static void delta(double* x, int* xd, const double* p, double t, int ev) {}
     // (F, 1) / (1/x) = (±x, x)
     PDMP_DEV static void chv_field(double* dy, const double* y, const int* xd, const double* p) {
-        dy[0] = (xd[0] & 1) ? -y[0] : y[0];
+        const double sg = (double)(1 - 2 * (xd[0] & 1));  // hoisted out of the stage loop by the compiler
+        dy[0] = sg * y[0];
         dy[1] = y[0];
     }
 };

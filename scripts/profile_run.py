@@ -1,0 +1,33 @@
+"""Small fixed workload for ncu: the C2 kernel variant (TCP CHV, records + stats) on 2^20
+trajectories, two runs (the first warms up).  Usage: python scripts/profile_run.py [model]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import pdmp_b200 as P
+
+model = sys.argv[1] if len(sys.argv) > 1 else "tcp"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
+pol = int(os.environ.get("PDMP_TSTOP_POLICY", "0"))
+if model == "tcp":
+    pb = P.models.problem("tcp", tspan=(0.0, 200.0))
+    xc0 = 0.5 + np.random.default_rng(2024).random((n, 1))
+    ens = P.Ensemble(pb, P.CHVGPU("tcp"), trajectories=n, n_jumps=1000, sample_times=[50.0, 100.0, 150.0, 200.0],
+                     max_records=n * 172, xc0=xc0, tstop_policy=pol)
+elif model == "morris_lecar":
+    pb = P.models.problem("morris_lecar")
+    ens = P.Ensemble(pb, P.CHVGPU("morris_lecar"), trajectories=n, n_jumps=2200, max_records=n * 800)
+elif model == "tcp2d":
+    pb = P.models.problem("tcp2d", tspan=(0.0, 10.0))
+    ens = P.Ensemble(pb, P.CHVGPU("tcp2d"), trajectories=n, n_jumps=2000, no_records=True,
+                     sample_times=list(10.0 * np.arange(1, 17) / 16), hist=[(0, 0.0, 4.0), (1, 0.0, 4.0)], hist_bins=256)
+elif model == "sir_rejection":
+    pb = P.models.problem("sir_rejection")
+    ens = P.Ensemble(pb, P.RejectionGPU("sir_rejection"), trajectories=n, n_jumps=1000, max_records=n * 260)
+for seed in (0, 1):
+    ens.run(seed=seed)
+    c = ens.counters()
+    print(model, n, "JT", os.environ.get("PDMP_JUMP_THRESH"), "RT", os.environ.get("PDMP_REFILL_THRESH"), "pol", pol, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in c.items()},
+          "jumps/s", c["total_jumps"] / (c["kernel_ms"] * 1e-3))
