@@ -226,25 +226,30 @@ PDMP_DEV double rk_attempt(RHS&& f, const double (&u)[D], const double (&k1)[D],
 //   reject : h_next = h / min(1/qmin, q11 / gamma)
 // Works on EEst^2 (= e2 / D) to skip the square root.
 // ---------------------------------------------------------------------------------------
+PDMP_DEV float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+PDMP_DEV float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 struct PIController {
-    float qold;
-    PDMP_DEV void init() { qold = 1e-4f; }
+    // log2 of qold^2, qold = max(EEst_prev, 1e-4): the controller works in the log2 domain on
+    // EEst^2, so one MUFU.LG2 and one MUFU.EX2 per attempt and no square root
+    float lq2;
+    PDMP_DEV void init() { lq2 = -26.575424759f; }  // log2(1e-8)
     // returns the factor f such that h_next = h * f
+    //   accept : f = 1/q,  q = clamp(EEst^b1 / qold^b2 / gamma, 1/qmax, 1/qmin)
+    //   reject : f = 1/min(1/qmin, EEst^b1 / gamma)
     PDMP_DEV double step(double EEst2, bool accept) {
-        const float e2 = (float)EEst2;
-        float q11, q;
-        if (e2 == 0.0f) { q11 = 0.0f; q = 0.1f; }
-        else {
-            const float l = __log2f(e2);                       // log2(EEst^2)
-            q11 = exp2f(0.5f * 0.14f * l);                     // EEst^beta1
-            q = q11 * exp2f(-0.08f * __log2f(qold));           // / qold^beta2
-            q = fmaxf(0.1f, fminf(5.0f, q * (1.0f / 0.9f)));
-        }
+        const float l = lg2_approx((float)EEst2);            // log2(EEst^2); -inf for EEst = 0
+        const float lq11 = 0.07f * l;                        // log2(EEst^beta1), beta1 = 7/50
+        const float lg = 0.15200309344f;                     // -log2(gamma), gamma = 9/10
+        float lq;
         if (accept) {
-            qold = fmaxf(sqrtf(e2), 1e-4f);
-            return (double)__frcp_rn(q);
+            lq = lq11 - 0.04f * lq2 + lg;                    // beta2 = 2/25
+            lq = fminf(fmaxf(lq, -3.32192809489f), 2.32192809489f);   // [log2(1/10), log2(5)]
+            lq2 = fmaxf(l, -26.575424759f);                  // qold = max(EEst, 1e-4)
+        } else {
+            lq = fminf(lq11 + lg, 2.32192809489f);
         }
-        return (double)__frcp_rn(fminf(5.0f, q11 * (1.0f / 0.9f)));
+        return (double)ex2_approx(-lq);
     }
 };
 

@@ -171,13 +171,22 @@ struct Traj {
     PDMP_DEV void accumulate(const KParams& P, double* sstat, unsigned* shist, int j, const double* xc) {
         if constexpr (!STATS) return;
         const int C = P.n_comp, TC = P.n_sample * C;
+        if (P.stats_in_smem) {
 #pragma unroll
-        for (int c = 0; c < NC + ND; ++c) {
-            const double v = c < NC ? xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
-            double* base = P.stats_in_smem ? sstat : P.stats;
-            atomicAdd(base + j * C + c, 1.0);
-            atomicAdd(base + TC + j * C + c, v);
-            atomicAdd(base + 2 * TC + j * C + c, v * v);
+            for (int c = 0; c < NC + ND; ++c) {
+                const double v = c < NC ? xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
+                atomicAdd(sstat + j * C + c, 1.0);
+                atomicAdd(sstat + TC + j * C + c, v);
+                atomicAdd(sstat + 2 * TC + j * C + c, v * v);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC + ND; ++c) {
+                const double v = c < NC ? xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
+                atomicAdd(P.stats + j * C + c, 1.0);
+                atomicAdd(P.stats + TC + j * C + c, v);
+                atomicAdd(P.stats + 2 * TC + j * C + c, v * v);
+            }
         }
         for (int hh = 0; hh < P.hist_n; ++hh) {
             const int c = P.hist_comp[hh];
@@ -445,8 +454,8 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
     T tr;
     int st = LANE_DEAD;
     const unsigned lane = threadIdx.x & 31u;
-    unsigned c_attempts = 0, c_rejects = 0, c_aux = 0, c_jumps = 0, c_cands = 0;
-    unsigned long long g_attempts = 0;  // spill-over of the 32-bit attempt counter
+    unsigned long long c_attempts = 0;
+    unsigned c_rejects = 0, c_aux = 0, c_jumps = 0, c_cands = 0;
     const unsigned budget = (unsigned)min((long long)0x7fffffff, P.max_attempts);
 
     // Phase scheduler.  Every iteration the warp does ONE of three things, chosen warp-uniformly:
@@ -529,8 +538,10 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
                 if (accept) {
 #pragma unroll
                     for (int i = 0; i < D; ++i) { tr.y[i] = yn[i]; tr.k1[i] = k7[i]; }
+                    // tstop reached: exactly (clipped step) or within 100 eps (OrdinaryDiffEq's
+                    // floating-point snap; here step < rem, so the gap is rem - step)
                     double sn = tr.s + step;
-                    if (clipped || fabs(sn - tr.tstop) < 100.0 * 2.220446049250313e-16 * fmax(fabs(sn), fabs(tr.tstop))) {
+                    if (clipped || rem - step < 2.220446049250313e-14 * fabs(tr.tstop)) {
                         sn = tr.tstop;
                         st = LANE_WAIT;
                     }
@@ -542,11 +553,10 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
                 tr.h = hnext;
             }
         }
-        if (c_attempts > 0x40000000u) { g_attempts += c_attempts; c_attempts = 0; }
     }
 
     // ---- flush counters (warp reduce, one atomic per warp) and CTA statistics ----
-    unsigned long long v[CT_N] = {g_attempts + c_attempts, c_rejects, c_aux, c_jumps, c_cands};
+    unsigned long long v[CT_N] = {c_attempts, c_rejects, c_aux, c_jumps, c_cands};
 #pragma unroll
     for (int k = 0; k < CT_N; ++k) {
         unsigned long long x = v[k];
