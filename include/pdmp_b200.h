@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PDMP_ABI_VERSION 3
+#define PDMP_ABI_VERSION 4
 
 /* ---- enumerations ------------------------------------------------------------------ */
 
@@ -215,6 +215,13 @@ int32_t pdmp_ensemble_upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc
 /* Launch the ensemble kernel(s) with inputs resident in HBM.  `stream` is a cudaStream_t
  * passed as void* (NULL: the ensemble's own stream).  Asynchronous. */
 int32_t pdmp_ensemble_run(pdmp_ensemble* e, uint64_t seed, void* stream);
+/* The host-buffer step: upload initial conditions from HOST memory (NULL: keep the resident
+ * ones), run, and stream every chunk's results to pinned host staging while later chunks still
+ * compute (D2H overlaps the kernels).  Synchronous; `result` holds HOST views valid until the
+ * next run/destroy.  This is what pdmp_solve_ensemble does after creating the ensemble. */
+int32_t pdmp_ensemble_run_host(pdmp_ensemble* e, uint64_t seed, const double* xc0, int32_t xc0_per_traj,
+                               const int64_t* xd0, int32_t xd0_per_traj, int32_t fetch_records,
+                               pdmp_result* result);
 /* Wait for the run and fill `result` with HOST views (pinned staging owned by the
  * ensemble, valid until the next run/destroy).  fetch_records = 0 skips the trajectory
  * arrays (counts, status, statistics and counters only). */

@@ -1,11 +1,11 @@
-"""ctypes mirror of include/pdmp_b200.h (ABI version 3).
+"""ctypes mirror of include/pdmp_b200.h (ABI version 4).
 
 Pure declarations: no library is loaded here, so the oracle loader (oracle/oracle.py, test
 infrastructure) can share the struct layouts without touching the product library.
 """
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ALG_CHV, ALG_REJECTION = 0, 1
 ODE_DP5, ODE_TSIT5 = 0, 1
@@ -72,7 +72,7 @@ class Result(C.Structure):
 EXPORTS = [
     "pdmp_abi_version", "pdmp_last_error", "pdmp_device_count", "pdmp_model_count",
     "pdmp_model_info_by_id", "pdmp_model_lookup", "pdmp_solve_ensemble", "pdmp_result_free",
-    "pdmp_ensemble_create", "pdmp_ensemble_upload_ics", "pdmp_ensemble_run", "pdmp_ensemble_fetch",
+    "pdmp_ensemble_create", "pdmp_ensemble_upload_ics", "pdmp_ensemble_run", "pdmp_ensemble_run_host", "pdmp_ensemble_fetch",
     "pdmp_ensemble_stats_device", "pdmp_ensemble_counters", "pdmp_ensemble_destroy",
     "pdmp_fp64_peak_tflops",
 ]

@@ -37,6 +37,8 @@ def lib():
         L.pdmp_ensemble_upload_ics.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         L.pdmp_ensemble_run.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.pdmp_ensemble_fetch.argtypes = [C.c_void_p, C.c_int32, P(_abi.Result)]
+        L.pdmp_ensemble_run_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                             C.c_int32, P(_abi.Result)]
         L.pdmp_ensemble_stats_device.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_uint64), P(C.c_void_p),
                                                  P(C.c_uint64)]
         L.pdmp_ensemble_counters.argtypes = [C.c_void_p, P(_abi.Result)]

@@ -73,6 +73,14 @@ struct Pinned {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    cudaError_t reserve_exact(size_t n) {  // no headroom: for capacities that are already upper bounds
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
     ~Pinned() { if (p) cudaFreeHost(p); }
 };
 
@@ -80,49 +88,86 @@ struct Pinned {
 
 using namespace pdmp;
 
+struct AddULL {
+    __host__ __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a + b; }
+};
+
+// closes a chunk's offsets range (offsets[count] = start of the next chunk) and archives the
+// number of pool blocks the chunk asked for
+__global__ void chunk_close_kernel(const unsigned long long* nrec, unsigned long long* offsets, unsigned long long count,
+                                   const unsigned long long* blk_src, unsigned long long* blk_dst) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (offsets) offsets[count] = offsets[count - 1] + nrec[count - 1];
+        blk_dst[0] = blk_src[0];
+    }
+}
+
+// A run is a pipeline of CHUNKS of trajectories.  NS compute streams take turns (kernel k+1
+// fills the SMs as the persistent CTAs of kernel k retire, which hides the tail of the
+// heavy-tailed jump counts), each with its own small record pool that is reused every other
+// chunk; the pool -> CSR compaction of chunk k and, in host mode, its D2H copy on a third
+// stream overlap the ensemble kernel of chunk k+1.
+constexpr int NS = 3;  // compute streams = chunks in flight = record pools
+
 struct pdmp_ensemble {
     int device = 0;
     const ModelEntry* m = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t cs[NS] = {};                 // compute
+    cudaStream_t copy = nullptr;              // D2H
     pdmp_solve_opts o{};
-    unsigned long long n = 0;
+    unsigned long long n = 0, chunk_n = 0;  // chunk_n: trajectories per chunk of a HOST-mode run
+    int n_chunks = 0;
+    bool shared_pool = false;  // one full-size pool for the whole ensemble (then resident runs are ONE kernel)
+    int cur_chunks = 1; unsigned long long cur_chunk_n = 0;  // chunking of the last run
     KParams P{};
     bool records = false, stats = false;
     int grid = 0;
     size_t smem = 0;
     // device buffers
     double* d_xc0 = nullptr; long long* d_xd0 = nullptr; double* d_replay = nullptr; double* d_sample = nullptr;
-    double* d_stats = nullptr; unsigned long long* d_hist = nullptr; unsigned long long* d_ctl = nullptr;
-    unsigned char* d_pool = nullptr; unsigned int* d_segtab = nullptr;
-    unsigned long long* d_nrec = nullptr;  // [n+1], last = 0 (so the scan yields the total)
+    double* d_stats = nullptr; unsigned long long* d_hist = nullptr;
+    unsigned long long* d_ctl = nullptr;      // [NS][2] (cursor, blk) per compute stream, then CT_N counters
+    unsigned long long* d_blkhist = nullptr;  // [n_chunks] pool blocks requested per chunk
+    unsigned char* d_pool[NS] = {};
+    unsigned int* d_segtab = nullptr;
+    unsigned long long* d_nrec = nullptr;
     long long* d_njumps = nullptr; long long* d_nrej = nullptr; unsigned char* d_status = nullptr;
     unsigned long long* d_offsets = nullptr; double* d_time = nullptr; double* d_xc = nullptr; long long* d_xd = nullptr;
-    void* d_scan = nullptr; size_t scan_bytes = 0;
-    unsigned long long csr_cap = 0;
+    void* d_scan[NS] = {}; size_t scan_bytes = 0;
+    unsigned long long csr_cap = 0, pool_blocks = 0;
     size_t n_stats = 0, n_hist = 0;
+    // events
+    cudaEvent_t ev_fork = nullptr, ev_kbeg = nullptr, ev_kend[NS] = {}, ev_h2d[2] = {nullptr, nullptr},
+                ev_d2h[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_base, ev_done, ev_c0, ev_c1;
     // host staging (pinned)
-    Pinned<unsigned long long> h_offsets, h_hist, h_ctl;
+    Pinned<unsigned long long> h_offsets, h_hist, h_ctl, h_bound, h_blk;
     Pinned<double> h_time, h_xc, h_stats;
     Pinned<long long> h_xd, h_njumps, h_nrej;
     Pinned<unsigned char> h_status;
-    bool ran = false;
+    bool ran = false, host_mode_done = false, host_records = false;
     float ms_kernel = 0, ms_compact = 0;
     double ms_h2d = 0, ms_d2h = 0;
     cudaStream_t last_stream = nullptr;
 
     ~pdmp_ensemble() {
         cudaSetDevice(device);
-        void* bufs[] = {d_xc0, d_xd0, d_replay, d_sample, d_stats, d_hist, d_ctl, d_pool, d_segtab, d_nrec,
-                        d_njumps, d_nrej, d_status, d_offsets, d_time, d_xc, d_xd, d_scan};
+        cudaDeviceSynchronize();
+        void* bufs[] = {d_xc0, d_xd0, d_replay, d_sample, d_stats, d_hist, d_ctl, d_blkhist, d_segtab,
+                        d_nrec, d_njumps, d_nrej, d_status, d_offsets, d_time, d_xc, d_xd};
         for (void* b : bufs) if (b) cudaFree(b);
-        for (auto& e : ev) if (e) cudaEventDestroy(e);
-        if (stream) cudaStreamDestroy(stream);
+        for (int q = 0; q < NS; ++q) { if (d_pool[q]) cudaFree(d_pool[q]); if (d_scan[q]) cudaFree(d_scan[q]); }
+        cudaEvent_t evs[] = {ev_fork, ev_kbeg, ev_h2d[0], ev_h2d[1], ev_d2h[0], ev_d2h[1]};
+        for (auto e : evs) if (e) cudaEventDestroy(e);
+        for (auto e : ev_kend) if (e) cudaEventDestroy(e);
+        for (auto* v : {&ev_base, &ev_done, &ev_c0, &ev_c1}) for (auto e : *v) if (e) cudaEventDestroy(e);
+        for (auto st : cs) if (st) cudaStreamDestroy(st);
+        if (copy) cudaStreamDestroy(copy);
     }
 };
 
-// d_ctl layout (unsigned long long): [0] work cursor, [1] block cursor, [2..2+CT_N) counters
-enum { CTL_CURSOR = 0, CTL_BLK = 1, CTL_CT = 2, CTL_N = 2 + CT_N };
+// d_ctl layout (unsigned long long): [2*s + 0] work cursor, [2*s + 1] block cursor of compute stream s; counters after
+enum { CTL_SHARED_BLK = 2 * NS, CTL_CT = 2 * NS + 1, CTL_N = 2 * NS + 1 + CT_N };
 
 extern "C" {
 
@@ -177,9 +222,27 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     auto* e = new pdmp_ensemble();
     std::unique_ptr<pdmp_ensemble> guard(e);
     e->device = o->device; e->m = &m; e->o = *o; e->n = d->n_traj;
-    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    for (auto& v : e->ev) CK(cudaEventCreate(&v));
+    for (auto& st : e->cs) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+    for (cudaEvent_t* ev : {&e->ev_kbeg, &e->ev_h2d[0], &e->ev_h2d[1], &e->ev_d2h[0], &e->ev_d2h[1]}) CK(cudaEventCreate(ev));
+    for (auto& ev : e->ev_kend) CK(cudaEventCreate(&ev));
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     const unsigned long long n = d->n_traj;
+    {   // chunking of the ensemble
+        const char* ec = std::getenv("PDMP_CHUNK");
+        const unsigned long long target = ec ? std::max<unsigned long long>(1024, std::strtoull(ec, nullptr, 10)) : (1ull << 20);
+        const unsigned long long nch = n <= 2 * target ? 1 : (n + target - 1) / target;
+        e->n_chunks = (int)std::max<unsigned long long>(nch, 1);
+        e->chunk_n = n ? (n + e->n_chunks - 1) / e->n_chunks : 1;
+        e->n_chunks = n ? (int)((n + e->chunk_n - 1) / e->chunk_n) : 1;
+    }
+    for (auto* v : {&e->ev_base, &e->ev_done, &e->ev_c0, &e->ev_c1}) v->assign(e->n_chunks, nullptr);
+    for (int k = 0; k < e->n_chunks; ++k) {
+        CK(cudaEventCreateWithFlags(&e->ev_base[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
+        CK(cudaEventCreate(&e->ev_c0[k])); CK(cudaEventCreate(&e->ev_c1[k]));
+    }
+    cudaStream_t s0 = e->cs[0];
     KParams& P = e->P;
     P.n_traj = n; P.traj_id_offset = d->traj_id_offset;
     P.xc0_per_traj = d->xc0_per_traj; P.xd0_per_traj = d->xd0_per_traj;
@@ -209,13 +272,13 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     const size_t nxc = (size_t)(d->xc0_per_traj ? n : 1) * NC, nxd = (size_t)(d->xd0_per_traj ? n : 1) * ND;
     CK(cudaMalloc(&e->d_xc0, std::max<size_t>(n, 1) * NC * sizeof(double)));
     CK(cudaMalloc(&e->d_xd0, std::max<size_t>(n, 1) * ND * sizeof(long long)));
-    CK(cudaMemcpyAsync(e->d_xc0, d->xc0, nxc * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_xd0, d->xd0, nxd * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_xc0, d->xc0, nxc * sizeof(double), cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(e->d_xd0, d->xd0, nxd * sizeof(long long), cudaMemcpyHostToDevice, s0));
     P.xc0 = e->d_xc0; P.xd0 = e->d_xd0;
     if (o->rng_mode == PDMP_RNG_REPLAY) {
         const size_t nr = (size_t)n * o->replay_stride;
         CK(cudaMalloc(&e->d_replay, std::max<size_t>(nr, 1) * sizeof(double)));
-        CK(cudaMemcpyAsync(e->d_replay, o->replay_u, nr * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->d_replay, o->replay_u, nr * sizeof(double), cudaMemcpyHostToDevice, s0));
         P.replay_u = e->d_replay;
     }
     if (e->stats) {
@@ -226,8 +289,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
                 return fail(PDMP_ERR_INVALID, "sample_times must be increasing and within (t0, tf]");
         }
         CK(cudaMalloc(&e->d_sample, o->n_sample_times * sizeof(double)));
-        CK(cudaMemcpyAsync(e->d_sample, o->sample_times, o->n_sample_times * sizeof(double), cudaMemcpyHostToDevice,
-                           e->stream));
+        CK(cudaMemcpyAsync(e->d_sample, o->sample_times, o->n_sample_times * sizeof(double), cudaMemcpyHostToDevice, s0));
         P.sample_times = e->d_sample;
         for (int h = 0; h < o->hist_n; ++h) {
             if (o->hist_comp[h] < 0 || o->hist_comp[h] >= NC + ND || !(o->hist_hi[h] > o->hist_lo[h]))
@@ -249,58 +311,96 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     e->smem = P.stats_in_smem ? smem_need : 0;
 
     CK(cudaMalloc(&e->d_ctl, CTL_N * sizeof(unsigned long long)));
-    P.cursor = e->d_ctl + CTL_CURSOR; P.blk_cursor = e->d_ctl + CTL_BLK; P.counters = e->d_ctl + CTL_CT;
+    CK(cudaMalloc(&e->d_blkhist, e->n_chunks * sizeof(unsigned long long)));
+    P.counters = e->d_ctl + CTL_CT;
     CK(cudaMalloc(&e->d_nrec, (n + 1) * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(e->d_nrec, 0, (n + 1) * sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(e->d_nrec, 0, (n + 1) * sizeof(unsigned long long), s0));
     CK(cudaMalloc(&e->d_njumps, std::max<size_t>(n, 1) * sizeof(long long)));
     CK(cudaMalloc(&e->d_nrej, std::max<size_t>(n, 1) * sizeof(long long)));
     CK(cudaMalloc(&e->d_status, std::max<size_t>(n, 1)));
     P.nrec = e->d_nrec; P.njumps = e->d_njumps; P.nrejected = e->d_nrej; P.status = e->d_status;
 
-    // record pool + CSR
+    // record pools (one per compute stream, sized for one chunk) + resident CSR
     if (e->records) {
         const unsigned long long maxrec = max_records_per_traj(*o);
         P.table_w = table_width(maxrec);
         const size_t rec_bytes = (size_t)m.rec_words * 8;
         const size_t csr_bytes = (size_t)8 * (1 + NC + ND);
+        const unsigned long long per_traj_worst = pool_records_for(maxrec);
+        const unsigned long long worst = n * per_traj_worst;
+        int npools = std::min(NS, e->n_chunks);
+        const double chunk_frac = n ? (double)e->chunk_n / (double)n : 1.0;
         unsigned long long want = o->max_records;
-        const unsigned long long worst = n * pool_records_for(maxrec);
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         const size_t fixed = (size_t)n * P.table_w * 4 + (n + 1) * 16 + (64u << 20);
         if (want == 0) {
             const size_t budget = free_b > fixed ? (size_t)((free_b - fixed) * 0.85) : 0;
-            want = std::min<unsigned long long>(worst, budget / (rec_bytes + csr_bytes));
+            const double per_rec = csr_bytes + rec_bytes * npools * chunk_frac * 1.06;
+            want = std::min<unsigned long long>(worst, (unsigned long long)(budget / per_rec));
         }
         want = std::min(std::max<unsigned long long>(want, std::min<unsigned long long>(worst, n * REC_BLOCK)), worst);
-        P.pool_blocks = (want + REC_BLOCK - 1) / REC_BLOCK;
-        const size_t pool_bytes = (size_t)P.pool_blocks * REC_BLOCK * rec_bytes;
-        e->csr_cap = P.pool_blocks * REC_BLOCK;
-        if (pool_bytes + e->csr_cap * csr_bytes + fixed > free_b)
-            return fail(PDMP_ERR_CAPACITY, "record pool + CSR (" + std::to_string((pool_bytes + e->csr_cap * csr_bytes) >> 20) +
+        // Preferred layout: ONE pool for the whole ensemble, if it fits next to the CSR in 60% of
+        // the free memory.  Device-resident runs are then a single persistent kernel (one tail
+        // instead of one per chunk) and host-mode chunks simply share the pool.
+        e->shared_pool = e->n_chunks == 1 ||
+                         ((double)want * (rec_bytes + csr_bytes) + fixed < 0.6 * (double)free_b && !std::getenv("PDMP_NO_SHARED_POOL"));
+        unsigned long long pool_rec;
+        if (e->shared_pool) {
+            npools = 1;
+            pool_rec = want;
+            e->csr_cap = want;
+        } else {
+            pool_rec = (unsigned long long)std::ceil((double)want * chunk_frac * 1.06);
+            pool_rec = std::max<unsigned long long>(pool_rec, e->chunk_n * REC_BLOCK);
+            pool_rec = std::min<unsigned long long>(pool_rec, e->chunk_n * per_traj_worst);
+        }
+        e->pool_blocks = (pool_rec + REC_BLOCK - 1) / REC_BLOCK;
+        // the CSR must hold whatever the pools can hold (a chunk never stores more than its pool)
+        if (!e->shared_pool)
+            e->csr_cap = std::min<unsigned long long>(worst, e->pool_blocks * REC_BLOCK * (unsigned long long)e->n_chunks);
+        const size_t pool_bytes = (size_t)e->pool_blocks * REC_BLOCK * rec_bytes;
+        if (pool_bytes * npools + e->csr_cap * csr_bytes + fixed > free_b)
+            return fail(PDMP_ERR_CAPACITY, "record pools + CSR (" +
+                                               std::to_string((pool_bytes * npools + e->csr_cap * csr_bytes) >> 20) +
                                                " MiB) exceed free device memory; lower max_records or shard the ensemble");
-        CK(cudaMalloc(&e->d_pool, std::max<size_t>(pool_bytes, 16)));
+        for (int q = 0; q < npools; ++q) CK(cudaMalloc(&e->d_pool[q], std::max<size_t>(pool_bytes, 16)));
         CK(cudaMalloc(&e->d_segtab, std::max<size_t>((size_t)n * P.table_w, 1) * sizeof(unsigned)));
         CK(cudaMalloc(&e->d_offsets, (n + 1) * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(e->d_offsets, 0, sizeof(unsigned long long), s0));
         CK(cudaMalloc(&e->d_time, std::max<size_t>(e->csr_cap, 1) * sizeof(double)));
         CK(cudaMalloc(&e->d_xc, std::max<size_t>(e->csr_cap * NC, 1) * sizeof(double)));
         CK(cudaMalloc(&e->d_xd, std::max<size_t>(e->csr_cap * ND, 1) * sizeof(long long)));
-        P.pool = e->d_pool; P.seg_table = e->d_segtab;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, e->scan_bytes, e->d_nrec, e->d_offsets, (long long)(n + 1), e->stream));
-        CK(cudaMalloc(&e->d_scan, std::max<size_t>(e->scan_bytes, 16)));
+        P.seg_table = e->d_segtab; P.pool_blocks = e->pool_blocks;
+        CK(cub::DeviceScan::ExclusiveScan(nullptr, e->scan_bytes, e->d_nrec, e->d_offsets, AddULL(),
+                                          cub::FutureValue<unsigned long long>(e->d_offsets), (long long)n, s0));
+        for (int q = 0; q < std::min(NS, e->n_chunks); ++q) CK(cudaMalloc(&e->d_scan[q], std::max<size_t>(e->scan_bytes, 16)));
     } else {
         P.table_w = 1; P.pool_blocks = 0;
     }
 
-    // persistent launch shape: resident CTAs per SM x SM count, capped by the work
+    // persistent launch shape: resident CTAs per SM x SM count, capped by the work of a chunk
     int bps = 0, sms = 0;
     CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, e->smem, &bps));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
     if (bps < 1) return fail(PDMP_ERR_CUDA, "kernel does not fit on an SM");
-    const unsigned long long need_blocks = (n + BLOCK - 1) / BLOCK;
-    e->grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)bps * sms, need_blocks));
-    CK(cudaStreamSynchronize(e->stream));  // inputs are borrowed only for the duration of the call
+    e->grid = std::max(1, bps * sms);
+    CK(cudaStreamSynchronize(s0));  // inputs are borrowed only for the duration of the call
     *out = guard.release();
+    return PDMP_OK;
+}
+
+static int upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc0_per_traj, const int64_t* xd0, int32_t xd0_per_traj,
+                      cudaStream_t st) {
+    const int NC = e->m->info.n_c, ND = e->m->info.n_d;
+    if (xc0) {
+        CK(cudaMemcpyAsync(e->d_xc0, xc0, (size_t)(xc0_per_traj ? e->n : 1) * NC * sizeof(double), cudaMemcpyHostToDevice, st));
+        e->P.xc0_per_traj = xc0_per_traj;
+    }
+    if (xd0) {
+        CK(cudaMemcpyAsync(e->d_xd0, xd0, (size_t)(xd0_per_traj ? e->n : 1) * ND * sizeof(long long), cudaMemcpyHostToDevice, st));
+        e->P.xd0_per_traj = xd0_per_traj;
+    }
     return PDMP_OK;
 }
 
@@ -308,48 +408,134 @@ int32_t pdmp_ensemble_upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc
                                  int32_t xd0_per_traj) {
     if (!e) return fail(PDMP_ERR_INVALID, "null ensemble");
     CK(cudaSetDevice(e->device));
+    int rc = upload_ics(e, xc0, xc0_per_traj, xd0, xd0_per_traj, e->cs[0]);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(e->cs[0]));  // the host arrays are borrowed only for the call
+    return PDMP_OK;
+}
+
+// D2H of chunk k's slice of every per-trajectory and per-record array (host mode)
+static int queue_chunk_d2h(pdmp_ensemble* e, int k, bool fetch_records) {
+    const unsigned long long a = (unsigned long long)k * e->cur_chunk_n, b = std::min(e->n, a + e->cur_chunk_n);
     const int NC = e->m->info.n_c, ND = e->m->info.n_d;
-    if (xc0) {
-        CK(cudaMemcpyAsync(e->d_xc0, xc0, (size_t)(xc0_per_traj ? e->n : 1) * NC * sizeof(double),
-                           cudaMemcpyHostToDevice, e->stream));
-        e->P.xc0_per_traj = xc0_per_traj;
+    CK(cudaEventSynchronize(e->ev_done[k]));  // chunk compacted; its record range is now known on the host
+    cudaStream_t st = e->copy;
+    CK(cudaStreamWaitEvent(st, e->ev_done[k], 0));
+    CK(cudaMemcpyAsync(e->h_njumps.p + a, e->d_njumps + a, (b - a) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(e->h_nrej.p + a, e->d_nrej + a, (b - a) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(e->h_status.p + a, e->d_status + a, (b - a), cudaMemcpyDeviceToHost, st));
+    if (fetch_records && e->records) {
+        const unsigned long long r0 = e->h_bound.p[k], r1 = e->h_bound.p[k + 1];
+        CK(cudaMemcpyAsync(e->h_offsets.p + a, e->d_offsets + a, (b - a + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if (r1 > r0) {
+            CK(cudaMemcpyAsync(e->h_time.p + r0, e->d_time + r0, (r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(e->h_xc.p + r0 * NC, e->d_xc + r0 * NC, (r1 - r0) * NC * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(e->h_xd.p + r0 * ND, e->d_xd + r0 * ND, (r1 - r0) * ND * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        }
     }
-    if (xd0) {
-        CK(cudaMemcpyAsync(e->d_xd0, xd0, (size_t)(xd0_per_traj ? e->n : 1) * ND * sizeof(long long),
-                           cudaMemcpyHostToDevice, e->stream));
-        e->P.xd0_per_traj = xd0_per_traj;
+    return PDMP_OK;
+}
+
+// The pipeline.  `user` (may be null) is the stream the caller orders the run on; host_mode
+// additionally streams every chunk's results to the pinned staging while later chunks compute.
+static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool host_mode, bool fetch_records) {
+    cudaStream_t s0 = user ? user : e->cs[0];
+    e->last_stream = s0;
+    e->P.seed = seed;
+    e->host_mode_done = false;
+    const int NC = e->m->info.n_c, ND = e->m->info.n_d;
+    if (host_mode) {
+        CK(e->h_njumps.reserve(e->n)); CK(e->h_nrej.reserve(e->n)); CK(e->h_status.reserve(e->n));
+        if (fetch_records && e->records) {
+            CK(e->h_offsets.reserve(e->n + 1)); CK(e->h_time.reserve_exact(e->csr_cap));
+            CK(e->h_xc.reserve_exact(e->csr_cap * NC)); CK(e->h_xd.reserve_exact(e->csr_cap * ND));
+        }
     }
+    CK(e->h_bound.reserve(e->n_chunks + 1)); CK(e->h_blk.reserve(e->n_chunks)); CK(e->h_ctl.reserve(CTL_N));
+    e->h_bound.p[0] = 0;
+    CK(cudaMemsetAsync(e->d_ctl, 0, CTL_N * sizeof(unsigned long long), s0));
+    if (e->n_stats) CK(cudaMemsetAsync(e->d_stats, 0, e->n_stats * sizeof(double), s0));
+    if (e->n_hist) CK(cudaMemsetAsync(e->d_hist, 0, e->n_hist * sizeof(unsigned long long), s0));
+    // fork: both compute streams start after everything already ordered on s0
+    CK(cudaEventRecord(e->ev_fork, s0));
+    for (auto st : e->cs) if (st != s0) CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
+    CK(cudaEventRecord(e->ev_kbeg, e->cs[0]));
+    // resident runs over a shared pool are ONE persistent kernel; host-mode runs (and runs whose
+    // pools are per-stream) are chunked so that compaction / D2H of chunk k overlap chunk k+1
+    const int nch = (!host_mode && e->shared_pool) ? 1 : e->n_chunks;
+    const unsigned long long chn = nch == 1 ? std::max<unsigned long long>(e->n, 1) : e->chunk_n;
+    e->cur_chunks = nch; e->cur_chunk_n = chn;
+    for (int k = 0; k < nch && e->n; ++k) {
+        const int q = k % NS;
+        cudaStream_t st = e->cs[q];
+        const unsigned long long a = (unsigned long long)k * chn, b = std::min(e->n, a + chn);
+        KParams Pk = e->P;
+        Pk.n_traj = b - a;
+        Pk.traj_id_offset = e->P.traj_id_offset + a;
+        if (Pk.xc0_per_traj) Pk.xc0 += a * NC;
+        if (Pk.xd0_per_traj) Pk.xd0 += a * ND;
+        if (Pk.replay_u) Pk.replay_u += a * Pk.replay_stride;
+        Pk.cursor = e->d_ctl + 2 * q;
+        Pk.blk_cursor = e->shared_pool ? e->d_ctl + CTL_SHARED_BLK : e->d_ctl + 2 * q + 1;
+        Pk.pool = e->d_pool[e->shared_pool ? 0 : q];
+        Pk.seg_table = e->d_segtab ? e->d_segtab + a * Pk.table_w : nullptr;
+        Pk.nrec += a; Pk.njumps += a; Pk.nrejected += a; Pk.status += a;
+        if (k >= NS) CK(cudaMemsetAsync(e->d_ctl + 2 * q, 0, 2 * sizeof(unsigned long long), st));
+        const int grid = (int)std::min<unsigned long long>(e->grid, (Pk.n_traj + BLOCK - 1) / BLOCK);
+        CK(e->m->launch(e->o.algorithm, e->o.ode, e->records, e->stats, Pk, std::max(grid, 1), e->smem, st));
+        CK(cudaEventRecord(e->ev_kend[q], st));
+        if (e->records && k > 0) CK(cudaStreamWaitEvent(st, e->ev_base[k - 1], 0));  // offsets[a] (start of this chunk) is final
+        CK(cudaEventRecord(e->ev_c0[k], st));
+        if (e->records) {
+            CK(cub::DeviceScan::ExclusiveScan(e->d_scan[q], e->scan_bytes, e->d_nrec + a, e->d_offsets + a,
+                                              AddULL(), cub::FutureValue<unsigned long long>(e->d_offsets + a),
+                                              (long long)(b - a), st));
+            chunk_close_kernel<<<1, 32, 0, st>>>(e->d_nrec + a, e->d_offsets + a, b - a, Pk.blk_cursor, e->d_blkhist + k);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e->ev_base[k], st));
+            CK(e->m->compact(Pk, e->d_offsets + a, e->d_time, e->d_xc, e->d_xd, st));
+            CK(cudaMemcpyAsync(e->h_bound.p + k + 1, e->d_offsets + b, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        } else {
+            chunk_close_kernel<<<1, 32, 0, st>>>(nullptr, nullptr, 0, Pk.blk_cursor, e->d_blkhist + k);
+            CK(cudaGetLastError());
+        }
+        CK(cudaEventRecord(e->ev_c1[k], st));
+        CK(cudaEventRecord(e->ev_done[k], st));
+        if (host_mode && k >= 1) { int rc = queue_chunk_d2h(e, k - 1, fetch_records); if (rc) return rc; }
+    }
+    if (host_mode && e->n) { int rc = queue_chunk_d2h(e, nch - 1, fetch_records); if (rc) return rc; }
+    // join: the caller's stream continues after both compute streams
+    if (e->n) for (int k = std::max(0, nch - NS); k < nch; ++k) CK(cudaStreamWaitEvent(s0, e->ev_done[k], 0));
+    e->ran = true;
+    e->host_records = host_mode && fetch_records;
+    e->host_mode_done = host_mode;
     return PDMP_OK;
 }
 
 int32_t pdmp_ensemble_run(pdmp_ensemble* e, uint64_t seed, void* stream) {
     if (!e) return fail(PDMP_ERR_INVALID, "null ensemble");
     CK(cudaSetDevice(e->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    if (stream) CK(cudaStreamSynchronize(e->stream));  // pending uploads were queued on our own stream
-    e->last_stream = st;
-    e->P.seed = seed;
-    CK(cudaMemsetAsync(e->d_ctl, 0, CTL_N * sizeof(unsigned long long), st));
-    if (e->n_stats) CK(cudaMemsetAsync(e->d_stats, 0, e->n_stats * sizeof(double), st));
-    if (e->n_hist) CK(cudaMemsetAsync(e->d_hist, 0, e->n_hist * sizeof(unsigned long long), st));
-    CK(cudaEventRecord(e->ev[0], st));
-    if (e->n) CK(e->m->launch(e->o.algorithm, e->o.ode, e->records, e->stats, e->P, e->grid, e->smem, st));
-    CK(cudaEventRecord(e->ev[1], st));
-    if (e->records && e->n) {
-        CK(cub::DeviceScan::ExclusiveSum(e->d_scan, e->scan_bytes, e->d_nrec, e->d_offsets, (long long)(e->n + 1), st));
-        CK(e->m->compact(e->P, e->d_offsets, e->d_time, e->d_xc, e->d_xd, st));
-    }
-    CK(cudaEventRecord(e->ev[2], st));
-    e->ran = true;
-    return PDMP_OK;
+    return run_pipeline(e, seed, (cudaStream_t)stream, false, false);
 }
 
 static int fill_counters(pdmp_ensemble* e, pdmp_result* r) {
-    CK(cudaStreamSynchronize(e->last_stream ? e->last_stream : e->stream));
+    CK(cudaStreamSynchronize(e->last_stream ? e->last_stream : e->cs[0]));
+    for (auto st : e->cs) CK(cudaStreamSynchronize(st));
     CK(e->h_ctl.reserve(CTL_N));
     CK(cudaMemcpy(e->h_ctl.p, e->d_ctl, CTL_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CK(cudaEventElapsedTime(&e->ms_kernel, e->ev[0], e->ev[1]));
-    CK(cudaEventElapsedTime(&e->ms_compact, e->ev[1], e->ev[2]));
+    CK(cudaMemcpy(e->h_blk.p, e->d_blkhist, e->cur_chunks * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    e->ms_kernel = 0;  // first kernel start -> last kernel end (kernels of the compute streams overlap)
+    for (int q = 0; q < std::min(NS, e->cur_chunks) && e->n; ++q) {
+        float kq = 0;
+        CK(cudaEventElapsedTime(&kq, e->ev_kbeg, e->ev_kend[q]));
+        e->ms_kernel = std::max(e->ms_kernel, kq);
+    }
+    e->ms_compact = 0;
+    for (int k = 0; k < e->cur_chunks && e->n; ++k) {
+        float c = 0;
+        CK(cudaEventElapsedTime(&c, e->ev_c0[k], e->ev_c1[k]));
+        e->ms_compact += c;
+    }
     std::memset(r, 0, sizeof(*r));
     r->n_traj = e->n;
     r->rk_attempts = e->h_ctl.p[CTL_CT + CT_ATTEMPTS];
@@ -360,13 +546,24 @@ static int fill_counters(pdmp_ensemble* e, pdmp_result* r) {
     r->kernel_ms = e->ms_kernel; r->compact_ms = e->ms_compact;
     r->n_sample_times = e->P.n_sample; r->n_comp = e->P.n_comp; r->hist_n = e->P.hist_n; r->hist_bins = e->P.hist_bins;
     r->n_c = e->m->info.n_c; r->n_d = e->m->info.n_d;
-    r->records_needed = e->h_ctl.p[CTL_BLK] * REC_BLOCK;
     if (e->records && e->n) {
         unsigned long long total = 0;
         CK(cudaMemcpy(&total, e->d_offsets + e->n, sizeof(total), cudaMemcpyDeviceToHost));
         r->total_records = total;
+        // capacity the run wanted: the worst chunk's pool demand, scaled to the whole CSR
+        unsigned long long worst_blk = 0;  // (shared pool: the cursor is cumulative, its last value is the demand)
+        for (int k = 0; k < e->cur_chunks; ++k) worst_blk = std::max(worst_blk, e->h_blk.p[k]);
+        r->records_needed = total;
+        if (worst_blk > e->pool_blocks)
+            r->records_needed = (unsigned long long)std::ceil((double)e->csr_cap * ((double)worst_blk / (double)e->pool_blocks));
     }
     return PDMP_OK;
+}
+
+static bool pool_overflowed(pdmp_ensemble* e) {
+    if (!e->records) return false;
+    for (int k = 0; k < e->cur_chunks; ++k) if (e->h_blk.p[k] > e->pool_blocks) return true;
+    return false;
 }
 
 int32_t pdmp_ensemble_counters(pdmp_ensemble* e, pdmp_result* r) {
@@ -374,6 +571,30 @@ int32_t pdmp_ensemble_counters(pdmp_ensemble* e, pdmp_result* r) {
     if (!e->ran) return fail(PDMP_ERR_INVALID, "ensemble has not run");
     CK(cudaSetDevice(e->device));
     return fill_counters(e, r);
+}
+
+static int fill_views(pdmp_ensemble* e, bool recs, pdmp_result* r) {
+    r->d2h_ms = e->ms_d2h; r->h2d_ms = e->ms_h2d;
+    r->njumps = (int64_t*)e->h_njumps.p; r->nrejected = (int64_t*)e->h_nrej.p; r->status = e->h_status.p;
+    r->stat_count = e->h_stats.p;
+    r->stat_sum = e->h_stats.p ? e->h_stats.p + e->n_stats / 3 : nullptr;
+    r->stat_sumsq = e->h_stats.p ? e->h_stats.p + 2 * (e->n_stats / 3) : nullptr;
+    r->hist = (uint64_t*)e->h_hist.p;
+    if (recs) {
+        r->offsets = (uint64_t*)e->h_offsets.p; r->time = e->h_time.p; r->xc = e->h_xc.p; r->xd = (int64_t*)e->h_xd.p;
+    }
+    if (pool_overflowed(e))
+        return fail(PDMP_ERR_CAPACITY, "record pool exhausted: about " + std::to_string(r->records_needed) +
+                                           " record slots needed, " + std::to_string(e->csr_cap) +
+                                           " configured; truncated trajectories carry status OUTPUT_OVERFLOW");
+    return PDMP_OK;
+}
+
+static int fetch_stats(pdmp_ensemble* e, cudaStream_t st) {
+    CK(e->h_stats.reserve(e->n_stats)); CK(e->h_hist.reserve(e->n_hist));
+    if (e->n_stats) CK(cudaMemcpyAsync(e->h_stats.p, e->d_stats, e->n_stats * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (e->n_hist) CK(cudaMemcpyAsync(e->h_hist.p, e->d_hist, e->n_hist * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    return PDMP_OK;
 }
 
 int32_t pdmp_ensemble_fetch(pdmp_ensemble* e, int32_t fetch_records, pdmp_result* r) {
@@ -384,18 +605,24 @@ int32_t pdmp_ensemble_fetch(pdmp_ensemble* e, int32_t fetch_records, pdmp_result
     if (rc) return rc;
     const size_t n = e->n;
     const int NC = e->m->info.n_c, ND = e->m->info.n_d;
-    cudaStream_t st = e->stream;
-    CK(cudaEventRecord(e->ev[3], st));
+    const bool recs = fetch_records && e->records && n;
+    if (e->host_mode_done && (e->host_records || !recs)) {
+        // the pipeline already streamed everything but the statistics
+        rc = fetch_stats(e, e->copy);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(e->copy));
+        return fill_views(e, recs, r);
+    }
+    cudaStream_t st = e->copy;
+    CK(cudaEventRecord(e->ev_d2h[0], st));
     CK(e->h_njumps.reserve(n)); CK(e->h_nrej.reserve(n)); CK(e->h_status.reserve(n));
-    CK(e->h_stats.reserve(e->n_stats)); CK(e->h_hist.reserve(e->n_hist));
     if (n) {
         CK(cudaMemcpyAsync(e->h_njumps.p, e->d_njumps, n * sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(e->h_nrej.p, e->d_nrej, n * sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(e->h_status.p, e->d_status, n, cudaMemcpyDeviceToHost, st));
     }
-    if (e->n_stats) CK(cudaMemcpyAsync(e->h_stats.p, e->d_stats, e->n_stats * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (e->n_hist) CK(cudaMemcpyAsync(e->h_hist.p, e->d_hist, e->n_hist * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    const bool recs = fetch_records && e->records && n;
+    rc = fetch_stats(e, st);
+    if (rc) return rc;
     const size_t total = recs ? (size_t)r->total_records : 0;
     if (recs) {
         CK(e->h_offsets.reserve(n + 1)); CK(e->h_time.reserve(total)); CK(e->h_xc.reserve(total * NC));
@@ -407,33 +634,28 @@ int32_t pdmp_ensemble_fetch(pdmp_ensemble* e, int32_t fetch_records, pdmp_result
             CK(cudaMemcpyAsync(e->h_xd.p, e->d_xd, total * ND * sizeof(long long), cudaMemcpyDeviceToHost, st));
         }
     }
+    CK(cudaEventRecord(e->ev_d2h[1], st));
     CK(cudaStreamSynchronize(st));
-    {
-        cudaEvent_t done;
-        CK(cudaEventCreate(&done));
-        CK(cudaEventRecord(done, st));
-        CK(cudaEventSynchronize(done));
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, e->ev[3], done));
-        cudaEventDestroy(done);
-        e->ms_d2h = ms;
-    }
-    r->d2h_ms = e->ms_d2h;
-    r->njumps = (int64_t*)e->h_njumps.p; r->nrejected = (int64_t*)e->h_nrej.p; r->status = e->h_status.p;
-    r->stat_count = e->h_stats.p;
-    r->stat_sum = e->h_stats.p ? e->h_stats.p + e->n_stats / 3 : nullptr;
-    r->stat_sumsq = e->h_stats.p ? e->h_stats.p + 2 * (e->n_stats / 3) : nullptr;
-    r->hist = (uint64_t*)e->h_hist.p;
-    if (recs) {
-        r->offsets = (uint64_t*)e->h_offsets.p; r->time = e->h_time.p; r->xc = e->h_xc.p; r->xd = (int64_t*)e->h_xd.p;
-    } else {
-        r->total_records = e->records ? r->total_records : 0;
-    }
-    if (e->records && e->h_ctl.p[CTL_BLK] > e->P.pool_blocks)
-        return fail(PDMP_ERR_CAPACITY, "record pool exhausted: " + std::to_string(r->records_needed) +
-                                           " record slots needed, " + std::to_string(e->csr_cap) +
-                                           " available; truncated trajectories carry status OUTPUT_OVERFLOW");
-    return PDMP_OK;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e->ev_d2h[0], e->ev_d2h[1]));
+    e->ms_d2h = ms;
+    return fill_views(e, recs, r);
+}
+
+int32_t pdmp_ensemble_run_host(pdmp_ensemble* e, uint64_t seed, const double* xc0, int32_t xc0_per_traj, const int64_t* xd0,
+                               int32_t xd0_per_traj, int32_t fetch_records, pdmp_result* r) {
+    if (!e || !r) return fail(PDMP_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaEventRecord(e->ev_h2d[0], e->cs[0]));
+    int rc = upload_ics(e, xc0, xc0_per_traj, xd0, xd0_per_traj, e->cs[0]);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->ev_h2d[1], e->cs[0]));
+    rc = run_pipeline(e, seed, nullptr, true, fetch_records != 0);
+    if (rc) return rc;
+    rc = pdmp_ensemble_fetch(e, fetch_records, r);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e->ev_h2d[0], e->ev_h2d[1]) == cudaSuccess) { e->ms_h2d = ms; r->h2d_ms = ms; }
+    return rc;
 }
 
 int32_t pdmp_ensemble_stats_device(pdmp_ensemble* e, void** stats_f64, uint64_t* n_f64, void** hist_u64, uint64_t* n_u64) {
@@ -453,9 +675,7 @@ int32_t pdmp_solve_ensemble(const pdmp_problem_desc* d, const pdmp_solve_opts* o
     pdmp_ensemble* e = nullptr;
     int rc = pdmp_ensemble_create(d, o, &e);
     if (rc) return rc;
-    rc = pdmp_ensemble_run(e, o->seed, nullptr);
-    if (rc) { delete e; return rc; }
-    rc = pdmp_ensemble_fetch(e, 1, r);
+    rc = pdmp_ensemble_run_host(e, o->seed, nullptr, 0, nullptr, 0, 1, r);
     if (rc && rc != PDMP_ERR_CAPACITY) { delete e; std::memset(r, 0, sizeof(*r)); return rc; }
     r->owner = e;  // the result views the ensemble's pinned staging
     return rc;

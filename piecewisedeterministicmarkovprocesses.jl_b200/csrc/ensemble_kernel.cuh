@@ -592,8 +592,11 @@ struct ModelEntry {
 
 // pool -> CSR: one warp per trajectory walks its segments; reads are 16-byte vector loads of
 // whole records, writes are contiguous runs per output array (time / xc / xd widened to int64)
+// Launch shape: 128 threads and at most 32 registers per thread, so that one compaction CTA
+// fits in the register space the resident ensemble CTAs leave free on every SM (e.g. TCP:
+// 6 x 128 x 80 = 61440 of 65536 registers) and the two kernels truly run concurrently.
 template <class M>
-__global__ void __launch_bounds__(256) compact_kernel(const KParams P, const unsigned long long* __restrict__ offsets,
+__global__ void __launch_bounds__(128, 16) compact_kernel(const KParams P, const unsigned long long* __restrict__ offsets,
                                                       double* __restrict__ time, double* __restrict__ xc,
                                                       long long* __restrict__ xd) {
     using RL = RecLayout<M>;
@@ -605,31 +608,32 @@ __global__ void __launch_bounds__(256) compact_kernel(const KParams P, const uns
         const unsigned n = (unsigned)P.nrec[i];
         const unsigned long long off = offsets[i];
         const unsigned* tab = P.seg_table + i * P.table_w;
-        unsigned seg_start = 0;  // first record index of segment k
-        for (int k = 0; seg_start < n; ++k) {
-            const unsigned cap = seg_records(k);
-            const unsigned cnt = min(cap, n - seg_start);
-            const unsigned long long slot0 = (unsigned long long)tab[k] * REC_BLOCK;
-            for (unsigned r = lane; r < cnt; r += 32) {
-                const double2* src = reinterpret_cast<const double2*>(P.pool + (slot0 + r) * RL::BYTES);
-                double w[RL::WORDS];
+        // record r lives in segment k = 4m + q / (16 << m) at position q % (16 << m), where
+        // m = floor(log2(r / 64 + 1)) is the size level and q = r - 64 (2^m - 1): every warp
+        // iteration moves 32 consecutive records whatever the segment boundaries
+        for (unsigned r = lane; r < n; r += 32) {
+            const unsigned m = 31u - __clz((r >> 6) + 1u);
+            const unsigned q = r - (64u << m) + 64u;
+            const unsigned k = 4u * m + (q >> (4u + m));
+            const unsigned pos = q & ((16u << m) - 1u);
+            const unsigned long long slot = (unsigned long long)__ldg(tab + k) * REC_BLOCK + pos;
+            const double2* src = reinterpret_cast<const double2*>(P.pool + slot * RL::BYTES);
+            double w[RL::WORDS];
 #pragma unroll
-                for (int q = 0; q < RL::WORDS / 2; ++q) {
-                    const double2 v = __ldcs(src + q);
-                    w[2 * q] = v.x; w[2 * q + 1] = v.y;
-                }
-                const unsigned long long o = off + seg_start + r;
-                __stcs(time + o, w[0]);
-#pragma unroll
-                for (int c = 0; c < NC; ++c) __stcs(xc + o * NC + c, w[1 + c]);
-#pragma unroll
-                for (int c = 0; c < ND; ++c) {
-                    const double pw = w[1 + NC + c / 2];
-                    const int v = (c & 1) ? __double2hiint(pw) : __double2loint(pw);
-                    __stcs(xd + o * ND + c, (long long)v);
-                }
+            for (int j = 0; j < RL::WORDS / 2; ++j) {
+                const double2 v = __ldcs(src + j);
+                w[2 * j] = v.x; w[2 * j + 1] = v.y;
             }
-            seg_start += cap;
+            const unsigned long long o = off + r;
+            __stcs(time + o, w[0]);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) __stcs(xc + o * NC + c, w[1 + c]);
+#pragma unroll
+            for (int c = 0; c < ND; ++c) {
+                const double pw = w[1 + NC + c / 2];
+                const int v = (c & 1) ? __double2hiint(pw) : __double2loint(pw);
+                __stcs(xd + o * ND + c, (long long)v);
+            }
         }
     }
 }
@@ -682,9 +686,9 @@ cudaError_t model_compact(const KParams& P, const unsigned long long* offsets, d
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    unsigned long long want = (P.n_traj + 7) / 8;  // 8 warps per CTA
-    const int grid = (int)std::min<unsigned long long>(want ? want : 1, (unsigned long long)sms * 8);
-    compact_kernel<M><<<grid, 256, 0, st>>>(P, offsets, time, xc, xd);
+    unsigned long long want = (P.n_traj + 3) / 4;  // 4 warps per CTA, one trajectory per warp at a time
+    const int grid = (int)std::min<unsigned long long>(want ? want : 1, (unsigned long long)sms * 16);
+    compact_kernel<M><<<grid, 128, 0, st>>>(P, offsets, time, xc, xd);
     return cudaGetLastError();
 }
 

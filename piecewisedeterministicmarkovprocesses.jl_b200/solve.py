@@ -81,7 +81,7 @@ class Ensemble:
         per_c = per_d = 0
         if xc0 is not None:
             xc = np.ascontiguousarray(xc0, dtype=np.float64)
-            per_c = int(xc.size == self.n_traj * self.info.n_c and xc.size != self.info.n_c or xc.ndim == 2)
+            per_c = int(xc.ndim == 2)
             pc = xc.ctypes.data
         if xd0 is not None:
             xd = np.ascontiguousarray(xd0, dtype=np.int64)
@@ -91,6 +91,27 @@ class Ensemble:
 
     def run(self, seed=0, stream=None):
         _lib.check(_lib.lib().pdmp_ensemble_run(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, stream))
+
+    def run_host(self, seed=0, xc0=None, xd0=None, records=True, copy=False):
+        """One host-buffer step: H2D of the initial conditions (host arrays; None keeps the resident
+        ones), the ensemble run, and D2H of every chunk's results overlapped with later chunks."""
+        xc = xd = None
+        pc = pd = None
+        per_c = per_d = 0
+        if xc0 is not None:
+            xc = np.ascontiguousarray(xc0, dtype=np.float64)
+            per_c = int(xc.ndim == 2)
+            pc = xc.ctypes.data
+        if xd0 is not None:
+            xd = np.ascontiguousarray(xd0, dtype=np.int64)
+            per_d = int(xd.ndim == 2)
+            pd = xd.ctypes.data
+        res = _abi.Result()
+        rc = _lib.lib().pdmp_ensemble_run_host(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, pc, per_c, pd, per_d,
+                                               int(bool(records)), C.byref(res))
+        _lib.check(rc)
+        return _marshal.to_numpy(res, copy=copy, save_positions=self._args["save_positions"],
+                                 sample_times=self._args.get("sample_times"), keep=self, records=records)
 
     def fetch(self, records=True, copy=False):
         res = _abi.Result()

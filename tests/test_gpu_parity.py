@@ -370,6 +370,30 @@ def test_resident_ensemble_handle(G):
     assert np.all(c.xc[c.offsets[:-1].astype(np.int64)] == [0.2, 0.3])
     cnt = ens.counters()
     assert cnt["total_records"] == len(c.time) and cnt["kernel_ms"] > 0
+    # host-buffer step: H2D + run + overlapped D2H in one call
+    d = ens.run_host(seed=1, xc0=xc0, copy=True)
+    assert np.array_equal(d.time, c.time) and np.array_equal(d.xd, c.xd) and np.array_equal(d.status, c.status)
+    ens.close()
+
+
+def test_chunked_pipeline_matches_single_chunk(G, monkeypatch):
+    # the run is a pipeline of chunks on two streams with alternating record pools; chunking
+    # must not change any result (Philox counters use the global trajectory id)
+    pb = G.models.problem("tcp", tspan=(0.0, 50.0))
+    n = 50_000
+    xc0 = 0.5 + np.random.default_rng(1).random((n, 1))
+    kw = dict(trajectories=n, n_jumps=300, seed=77, xc0=xc0, sample_times=[10.0, 50.0])
+    one = G.solve(pb, G.CHVGPU("tcp"), **kw)
+    monkeypatch.setenv("PDMP_CHUNK", "4096")       # 13 chunks (library reads it at ensemble creation)
+    many = G.solve(pb, G.CHVGPU("tcp"), **kw)
+    assert np.array_equal(one.offsets, many.offsets) and np.array_equal(one.time, many.time)
+    assert np.array_equal(one.xc, many.xc) and np.array_equal(one.xd, many.xd)
+    assert np.array_equal(one.status, many.status) and np.array_equal(one.njumps, many.njumps)
+    assert np.array_equal(one.stat_count, many.stat_count) and np.allclose(one.stat_sum, many.stat_sum, rtol=1e-12)
+    ens = G.Ensemble(pb, G.CHVGPU("tcp"), **{k: v for k, v in kw.items() if k != "seed"})
+    ens.run(seed=77)
+    dev = ens.fetch(copy=True)                     # device-resident run, one D2H at the end
+    assert np.array_equal(dev.time, one.time) and np.array_equal(dev.offsets, one.offsets)
     ens.close()
 
 
