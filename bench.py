@@ -184,16 +184,13 @@ def run_gpu(args):
     n = args.traj
     pb = P.models.problem("tcp", tspan=(0.0, TF))
     ics_t, ics = host_ics(n)
-    ens = P.Ensemble(pb, P.CHVGPU("tcp", ode="dp5"), trajectories=n, traj_id_offset=rank * n, n_jumps=N_JUMPS,
-                     reltol=RELTOL, abstol=ABSTOL, save_positions=(False, True), sample_times=SAMPLE_TIMES,
-                     device=local, max_records=int(n * 160), xc0=ics, tstop_policy=1)
+    mk = lambda ntr, ic: P.Ensemble(pb, P.CHVGPU("tcp", ode="dp5"), trajectories=ntr, traj_id_offset=rank * n,
+                                    n_jumps=N_JUMPS, reltol=RELTOL, abstol=ABSTOL, save_positions=(False, True),
+                                    sample_times=SAMPLE_TIMES, device=local, max_records=int(ntr * 160), xc0=ic,
+                                    tstop_policy=1)
+    ens = mk(n, ics)
     n_chunks = 1 if n <= 2 * (1 << 20) else -(-n // (1 << 20))
-    pf, nf, ph, nh = ens.stats_device()
-
-    class _Dev:  # zero-copy torch view of the library's statistics buffer (for NCCL)
-        def __init__(self, ptr, nelem):
-            self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-    stats_t = torch.as_tensor(_Dev(pf, nf), device=dev) if nf else None
+    stats_t, hist_t = P.distributed.stats_tensors(ens, dev)   # zero-copy torch views of the library's buffers
     stream = torch.cuda.current_stream().cuda_stream
 
     def step(seed):
@@ -236,16 +233,27 @@ def run_gpu(args):
     traj_per_s = float(tot[1].item()) / (ms_max * 1e-3)
 
     # ---- end to end through the host-buffer API (H2D ICs, step, D2H of everything) ----
+    # the pinned host staging holds every record of a step (~51 GB at 10^7 trajectories): bound it
+    # by the host memory actually available to this rank
+    stats_t = hist_t = None
+    ens.close()
+    import psutil
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    budget = 0.5 * psutil.virtual_memory().available / max(local_world, 1)
+    n_e2e = int(min(n, budget / (160 * 32.0 * 1.02)))
+    n_e2e = max(1 << 16, (n_e2e >> 16) << 16) if n_e2e < n else n
+    ens = mk(n_e2e, ics[:n_e2e])
+    ics_e = ics[:n_e2e]
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    r = ens.run_host(seed=999, xc0=ics)   # warm-up: allocates (pins) the host staging
-    d2h_bytes = (r.time.nbytes + r.xc.nbytes + r.xd.nbytes + r.offsets.nbytes + r.njumps.nbytes +
-                 r.nrejected.nbytes + r.status.nbytes + r.stat_count.nbytes * 3)
+    r = ens.run_host(seed=999, xc0=ics_e)   # warm-up: allocates (pins) the host staging
     del r
     barrier()
     t0 = time.perf_counter()
     ej = 0
     for s in range(e2e_steps):
-        r = ens.run_host(seed=s, xc0=ics)   # H2D ICs -> chunked kernels -> D2H of every record, overlapped
+        r = ens.run_host(seed=s, xc0=ics_e)   # H2D ICs -> chunked kernels -> D2H of every record, overlapped
+        if world > 1:
+            P.distributed.allreduce_stats_host(r)   # global statistics on every rank
         ej += r.counters["total_jumps"]
         d2h_bytes = (r.time.nbytes + r.xc.nbytes + r.xd.nbytes + r.offsets.nbytes + r.njumps.nbytes +
                      r.nrejected.nbytes + r.status.nbytes + r.stat_count.nbytes * 3)
@@ -275,8 +283,8 @@ def run_gpu(args):
             "trajectories_per_sec": traj_per_s,
             "jumps_per_step_rank0": jumps / args.steps, "records_per_step_rank0": records / args.steps,
             "rk_attempts_per_jump": attempts / max(jumps, 1),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ics.nbytes),
-                    "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ics_e.nbytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps, "trajectories_per_gpu": n_e2e,
                     "ms_per_step": 1e3 * float(e.item()) / e2e_steps},
             "gpu_launches": 3 * n_chunks * args.steps,
             "gpu_launches_note": f"per step: {n_chunks} chunks x (ensemble_kernel + chunk_close_kernel + compact_kernel), ours; "

@@ -6,12 +6,12 @@ Host-side mirror (Python, ctypes) of the reference's Julia surface; the compute 
 csrc/ (CUDA, sm_100a) behind the C ABI of include/pdmp_b200.h.  Importing this package
 does not load the CUDA library; the first solve does, and raises if it is missing.
 """
-from . import _abi, _marshal, models
+from . import _abi, _marshal, distributed, models
 from .algorithms import (AbstractCHV, AbstractPDMPAlgorithm, AbstractRejection, CHVGPU, RejectionGPU)
 from .problem import EnsembleResult, PDMPProblem, PDMPResult
 from .solve import Ensemble, solve
 from ._lib import PDMPError, device_count, fp64_peak_tflops, list_models, model_info
 
 __all__ = ["PDMPProblem", "PDMPResult", "EnsembleResult", "CHVGPU", "RejectionGPU", "solve", "Ensemble",
-           "models", "PDMPError", "device_count", "fp64_peak_tflops", "list_models", "model_info",
+           "models", "distributed", "PDMPError", "device_count", "fp64_peak_tflops", "list_models", "model_info",
            "AbstractPDMPAlgorithm", "AbstractCHV", "AbstractRejection"]

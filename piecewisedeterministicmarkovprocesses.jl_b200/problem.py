@@ -97,6 +97,7 @@ class EnsembleResult:
     counters: dict = field(default_factory=dict)
     save_positions: Tuple[bool, bool] = (False, True)
     sample_times: Optional[np.ndarray] = None
+    shard: Optional[Tuple[int, int]] = None   # (global id offset, count) when produced by solve_sharded
     _keep: Any = None
 
     def __len__(self):
