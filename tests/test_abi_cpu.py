@@ -74,3 +74,28 @@ def test_argument_validation(P, lib):
     with pytest.raises(P.PDMPError) as ei:
         P.solve(P.models.problem("tcp2d"), P.RejectionGPU("tcp2d"), trajectories=4, n_jumps=5)
     assert ei.value.code == P._abi.ERR_MODEL                       # no bound => no Rejection
+
+
+_JL2C = {"Int32": C.c_int32, "Int64": C.c_int64, "UInt64": C.c_uint64, "Float64": C.c_double,
+         "Ptr{Float64}": C.POINTER(C.c_double), "Ptr{Int64}": C.POINTER(C.c_int64),
+         "Ptr{UInt64}": C.POINTER(C.c_uint64), "Ptr{Int32}": C.POINTER(C.c_int32),
+         "Ptr{UInt8}": C.POINTER(C.c_uint8), "Ptr{Cvoid}": C.c_void_p, "NTuple{32, UInt8}": C.c_char * 32}
+
+
+def test_julia_binding_struct_layouts(P):
+    """julia/PDMPB200.jl cannot be executed here (no Julia runtime): keep its C struct mirrors in
+    lock-step with include/pdmp_b200.h by comparing them field by field with the ctypes mirror."""
+    src = open(os.path.join(ROOT, "julia", "PDMPB200.jl")).read()
+    assert f"const ABI_VERSION = {P._abi.ABI_VERSION}" in src
+    for jl, ct in [("ModelInfo", P._abi.ModelInfo), ("ProblemDesc", P._abi.ProblemDesc),
+                   ("SolveOpts", P._abi.SolveOpts), ("CResult", P._abi.Result)]:
+        body = re.search(r"struct %s\n(.*?)\n(?:    \w+\(\) = new\(\)\n)?end" % jl, src, re.S).group(1)
+        fields = re.findall(r"^\s+(\w+)::([\w{}, ]+)$", body, re.M)
+        assert [f for f, _ in fields] == [f for f, _ in ct._fields_], jl
+        for (name, jt), (_, ctype) in zip(fields, ct._fields_):
+            want = _JL2C[jt]
+            assert C.sizeof(want) == C.sizeof(ctype) and (want is ctype or want._type_ == ctype._type_), (jl, name)
+    # every entry point the binding ccalls is declared by the header
+    hdr = open(os.path.join(ROOT, "include", "pdmp_b200.h")).read()
+    for sym in set(re.findall(r"\(:(pdmp_\w+), libpdmp", src)):
+        assert re.search(r"\b%s\s*\(" % sym, hdr), sym
