@@ -41,7 +41,11 @@ UNIT = "jumps/s"
 TF, N_JUMPS, RELTOL, ABSTOL = 200.0, 1000, 1e-7, 1e-9
 SAMPLE_TIMES = [50.0, 100.0, 150.0, 200.0]
 FLOPS_PER_ATTEMPT_TCP = 180.0   # D*72 + 2 + 10 + 6*C_rhs, D = 2, C_rhs = 4
-REC_BYTES_TCP = 32.0            # 8*(1+n_c) + 8*n_d per saved point
+REC_BYTES_TCP = 32.0            # 8*(1+n_c) + 8*n_d per saved point; pool record
+CSR_BYTES_TCP = 20.0            # CSR / wire record with int16 xd transport: 8 + 8 + 2*2
+# DRAM bytes per saved record measured by `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum over the
+# records of that launch; profiles/r1_tcp_kernel_v3_full.txt, profiles/r1_compact_kernel_full.txt)
+NCU_DRAM_BYTES_PER_RECORD = {"ensemble_kernel": 33.1, "compact_kernel": 66.0}
 
 
 def workload_config(n_traj, n_gpus):
@@ -52,6 +56,8 @@ def workload_config(n_traj, n_gpus):
         "tstop_policy": "1 on the GPU: after a step clipped by a jump threshold the proposal never drops below the "
                         "pending unclipped one (every step stays error-controlled); the CPU arm keeps OrdinaryDiffEq's rule",
         "save_positions": [False, True], "sample_times": SAMPLE_TIMES,
+        "xd_transport": "auto -> int16 (|xd| <= 1 + 999 is provable for TCP with n_jumps = 1000; widened to the reference's "
+                        "Int64 per trajectory on access): a saved point is 8 (t) + 8 (xc) + 2 x 2 (xd) = 20 B on the wire",
         "initial_conditions": "synthetic xc0_i = 0.5 + u_i (numpy PCG64 seed 2024), xd0 = [0, 1]",
         "rng": "philox4x32-10, seed = step index",
         "l2": "working set (>= 40 GB of records per step) is far larger than the 126 MB L2; no flush needed",
@@ -187,7 +193,7 @@ def run_gpu(args):
     mk = lambda ntr, ic: P.Ensemble(pb, P.CHVGPU("tcp", ode="dp5"), trajectories=ntr, traj_id_offset=rank * n,
                                     n_jumps=N_JUMPS, reltol=RELTOL, abstol=ABSTOL, save_positions=(False, True),
                                     sample_times=SAMPLE_TIMES, device=local, max_records=int(ntr * 160), xc0=ic,
-                                    tstop_policy=1)
+                                    tstop_policy=1, xd_transport="auto")
     ens = mk(n, ics)
     n_chunks = 1 if n <= 2 * (1 << 20) else -(-n // (1 << 20))
     stats_t, hist_t = P.distributed.stats_tensors(ens, dev)   # zero-copy torch views of the library's buffers
@@ -240,7 +246,7 @@ def run_gpu(args):
     import psutil
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     budget = 0.5 * psutil.virtual_memory().available / max(local_world, 1)
-    n_e2e = int(min(n, budget / (160 * 32.0 * 1.02)))
+    n_e2e = int(min(n, budget / (160 * CSR_BYTES_TCP * 1.02)))
     n_e2e = max(1 << 16, (n_e2e >> 16) << 16) if n_e2e < n else n
     ens = mk(n_e2e, ics[:n_e2e])
     ics_e = ics[:n_e2e]
@@ -275,7 +281,7 @@ def run_gpu(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        comp_gbs = records * 2 * REC_BYTES_TCP / (compact_ms * 1e-3) / 1e9 if compact_ms > 0 else None
+        comp_gbs = records * (REC_BYTES_TCP + CSR_BYTES_TCP) / (compact_ms * 1e-3) / 1e9 if compact_ms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -290,13 +296,17 @@ def run_gpu(args):
             "gpu_launches_note": f"per step: {n_chunks} chunks x (ensemble_kernel + chunk_close_kernel + compact_kernel), ours; "
                                  "plus cub::DeviceScan per chunk and memsets",
             "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                         "traffic": None, "kernel": "ensemble_kernel<TcpDev,TabDP5,CHV,records,stats>",
+                         "traffic": NCU_DRAM_BYTES_PER_RECORD["ensemble_kernel"] * records / args.steps,
+                         "traffic_note": "bytes per launch = ncu-measured DRAM bytes per saved record (profiles/) x records of one "
+                                         "launch; algorithmic output bytes are 32 B/record, the integrator state never leaves registers",
+                         "kernel": "ensemble_kernel<TcpDev,TabDP5,CHV,records,stats>",
                          "peak_source": "live DFMA microbenchmark in libpdmp_b200.so (MEASURED_PEAKS.json has no FP64 entry)",
                          "algorithmic_flops_per_rk_attempt": FLOPS_PER_ATTEMPT_TCP,
                          "rk_attempts_per_step": attempts / args.steps, "kernel_ms_per_step": kernel_ms / args.steps},
             "roofline_output": {"bound": "hbm", "kernel": "compact_kernel<TcpDev> (pool -> CSR)", "achieved": comp_gbs,
                                 "peak": hbm_peak, "unit": "GB/s", "frac": (comp_gbs / hbm_peak) if comp_gbs else None,
-                                "algorithmic_bytes_per_record": 2 * REC_BYTES_TCP,
+                                "algorithmic_bytes_per_record": REC_BYTES_TCP + CSR_BYTES_TCP,
+                                "traffic": NCU_DRAM_BYTES_PER_RECORD["compact_kernel"] * records / args.steps,
                                 "compact_ms_per_step": compact_ms / args.steps,
                                 "note": "compact_ms also contains the offsets scan"},
             "clocks": clk,
@@ -319,7 +329,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--traj", type=int, default=10_000_000, help="trajectories per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_500_000, help="trajectories of the CPU baseline sample (~15 s on 16 cores)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

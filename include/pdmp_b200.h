@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PDMP_ABI_VERSION 4
+#define PDMP_ABI_VERSION 5
 
 /* ---- enumerations ------------------------------------------------------------------ */
 
@@ -147,7 +147,14 @@ typedef struct pdmp_solve_opts {
     int32_t ref_quirks;           /* oracle only: 1 reproduces the reference's last-bit at
                                      default tolerances 1e-3/1e-6 (src/chvdiffeq.jl:160-168)
                                      and the stale-xc last bit of rejection_diffeq!        */
-    int32_t reserved0;
+    int32_t xd_bytes;             /* width of the saved discrete states in result.xd:
+                                     0 or 8: int64 (the reference's Int64 layout)
+                                     4: int32 — always exact (the kernel holds xd as int32)
+                                     2: int16 — the caller asserts |xd| < 32768 for the whole
+                                        run (e.g. |xd0| + n_jumps max|nu| without a Delta);
+                                        the host bindings check this bound before asking.
+                                     Narrow transport cuts the device->host bytes per saved
+                                     point; the bindings widen per trajectory on access.    */
 } pdmp_solve_opts;
 
 /* ---- result ------------------------------------------------------------------------ */
@@ -162,7 +169,8 @@ typedef struct pdmp_result {
     uint64_t* offsets;         /* [n_traj+1]                                               */
     double* time;              /* [total_records]                                          */
     double* xc;                /* [total_records][n_c]                                     */
-    int64_t* xd;               /* [total_records][n_d]                                     */
+    void* xd;                  /* [total_records][n_d], elements of xd_bytes bytes (int64
+                                  unless opts.xd_bytes asked for a narrower transport)    */
     int64_t* njumps;           /* [n_traj] PDMPResult.njumps (src/utils.jl:79)             */
     int64_t* nrejected;        /* [n_traj] PDMPResult.nrejected (fictitous_jumps)          */
     uint8_t* status;           /* [n_traj] PDMP_ST_*                                       */
@@ -182,6 +190,7 @@ typedef struct pdmp_result {
     double h2d_ms, d2h_ms;
     int32_t n_sample_times, n_comp, hist_n, hist_bins;
     int32_t n_c, n_d;
+    int32_t xd_bytes, reserved0;
     void* owner;               /* private                                                  */
 } pdmp_result;
 

@@ -22,7 +22,7 @@ using Libdl
 
 export CHVGPU, RejectionGPU, EnsembleResult, device_count, list_models
 
-const ABI_VERSION = 4
+const ABI_VERSION = 5
 const libpdmp = Ref{String}(get(ENV, "PDMP_B200_LIB", "libpdmp_b200.so"))
 
 # ---- algorithm types ---------------------------------------------------------------------
@@ -111,7 +111,7 @@ struct SolveOpts
     device::Int32
     tstop_policy::Int32
     ref_quirks::Int32
-    reserved0::Int32
+    xd_bytes::Int32
 end
 
 mutable struct CResult
@@ -121,7 +121,7 @@ mutable struct CResult
     offsets::Ptr{UInt64}
     time::Ptr{Float64}
     xc::Ptr{Float64}
-    xd::Ptr{Int64}
+    xd::Ptr{Cvoid}
     njumps::Ptr{Int64}
     nrejected::Ptr{Int64}
     status::Ptr{UInt8}
@@ -144,6 +144,8 @@ mutable struct CResult
     hist_bins::Int32
     n_c::Int32
     n_d::Int32
+    xd_bytes::Int32
+    reserved0::Int32
     owner::Ptr{Cvoid}
     CResult() = new()
 end
@@ -207,6 +209,15 @@ end
 _copy(p::Ptr{T}, dims...) where {T} = (p == C_NULL || prod(dims) == 0) ? zeros(T, dims...) :
                                       copy(unsafe_wrap(Array, p, dims))
 
+# saved discrete states arrive as Int64, or narrower under `xd_bytes = 4 | 2` (less PCIe traffic);
+# they are widened here to the reference's Int64
+function _xd(res::CResult, tot::Int)
+    nd = Int(res.n_d)
+    (res.xd == C_NULL || tot == 0) && return zeros(Int64, nd, tot)
+    T = res.xd_bytes == 2 ? Int16 : res.xd_bytes == 4 ? Int32 : Int64
+    Matrix{Int64}(unsafe_wrap(Array, Ptr{T}(res.xd), (nd, tot)))
+end
+
 # ---- solve ----------------------------------------------------------------------------------
 """
     solve(problem::PDMPProblem, algo::Union{CHVGPU, RejectionGPU}; trajectories, n_jumps, kwargs...)
@@ -226,7 +237,7 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
                          reltol = 1e-7, abstol = 1e-9, seed::Integer = 0, replay = nothing,
                          sample_times = Float64[], hist = Tuple{Int, Float64, Float64}[], hist_bins = 0,
                          device = 0, traj_id_offset = 0, xc0 = nothing, xd0 = nothing, max_records = 0,
-                         no_records = false, max_attempts = 0, tstop_policy = 0,
+                         no_records = false, max_attempts = 0, tstop_policy = 0, xd_bytes = 8,
                          verbose = false, save_rate = false, finalizer = nothing, kwargs...)
     (n_jumps === nothing || !isfinite(n_jumps)) &&
         error("n_jumps must be given and finite for an ensemble solve")
@@ -255,7 +266,7 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
                       isempty(hlo) ? C_NULL : pointer(hlo), isempty(hhi) ? C_NULL : pointer(hhi), maxrec,
                       algorithm_code(algo), ode_code(algo), 0, isempty(ru) ? 0 : 1,
                       save_positions[1], save_positions[2], no_records, length(st), length(hc),
-                      isempty(hc) ? 0 : hist_bins, device, tstop_policy, 0, 0)
+                      isempty(hc) ? 0 : hist_bins, device, tstop_policy, 0, xd_bytes)
         end
         rc = ccall((:pdmp_solve_ensemble, libpdmp[]), Int32, (Ref{ProblemDesc}, Ref{SolveOpts}, Ref{CResult}),
                    desc, opts(max_records), res)
@@ -270,7 +281,7 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
     n, tot = Int(res.n_traj), Int(res.total_records)
     T, C, H, B = Int(res.n_sample_times), Int(res.n_comp), Int(res.hist_n), Int(res.hist_bins)
     out = EnsembleResult(_copy(res.offsets, n + 1), _copy(res.time, tot),
-                         _copy(res.xc, Int(res.n_c), tot), _copy(res.xd, Int(res.n_d), tot),
+                         _copy(res.xc, Int(res.n_c), tot), _xd(res, tot),
                          _copy(res.njumps, n), _copy(res.nrejected, n), _copy(res.status, n),
                          _copy(res.stat_count, C, T), _copy(res.stat_sum, C, T), _copy(res.stat_sumsq, C, T),
                          _copy(res.hist, B, H, T),

@@ -868,6 +868,7 @@ int run_ensemble(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_resu
     res->total_jumps = jumps; res->total_candidates = cands;
     res->n_sample_times = sh.T; res->n_comp = sh.C; res->hist_n = sh.H; res->hist_bins = sh.B;
     res->n_c = M::NC; res->n_d = M::ND;
+    res->xd_bytes = 8;  // the oracle always returns the reference's Int64 layout
     res->owner = own;
     return PDMP_OK;
 }

@@ -1,11 +1,11 @@
-"""ctypes mirror of include/pdmp_b200.h (ABI version 4).
+"""ctypes mirror of include/pdmp_b200.h (ABI version 5).
 
 Pure declarations: no library is loaded here, so the oracle loader (oracle/oracle.py, test
 infrastructure) can share the struct layouts without touching the product library.
 """
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ALG_CHV, ALG_REJECTION = 0, 1
 ODE_DP5, ODE_TSIT5 = 0, 1
@@ -50,12 +50,12 @@ class SolveOpts(C.Structure):
                 ("rng_mode", C.c_int32), ("save_pre", C.c_int32), ("save_post", C.c_int32),
                 ("no_records", C.c_int32), ("n_sample_times", C.c_int32), ("hist_n", C.c_int32),
                 ("hist_bins", C.c_int32), ("device", C.c_int32), ("tstop_policy", C.c_int32),
-                ("ref_quirks", C.c_int32), ("reserved0", C.c_int32)]
+                ("ref_quirks", C.c_int32), ("xd_bytes", C.c_int32)]
 
 
 class Result(C.Structure):
     _fields_ = [("n_traj", C.c_uint64), ("total_records", C.c_uint64), ("records_needed", C.c_uint64),
-                ("offsets", c_uint64_p), ("time", c_double_p), ("xc", c_double_p), ("xd", c_int64_p),
+                ("offsets", c_uint64_p), ("time", c_double_p), ("xc", c_double_p), ("xd", C.c_void_p),
                 ("njumps", c_int64_p), ("nrejected", c_int64_p), ("status", c_uint8_p),
                 ("stat_count", c_double_p), ("stat_sum", c_double_p), ("stat_sumsq", c_double_p),
                 ("hist", c_uint64_p),
@@ -65,6 +65,7 @@ class Result(C.Structure):
                 ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("n_sample_times", C.c_int32), ("n_comp", C.c_int32), ("hist_n", C.c_int32),
                 ("hist_bins", C.c_int32), ("n_c", C.c_int32), ("n_d", C.c_int32),
+                ("xd_bytes", C.c_int32), ("reserved0", C.c_int32),
                 ("owner", C.c_void_p)]
 
 

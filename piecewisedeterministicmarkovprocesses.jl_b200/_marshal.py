@@ -21,12 +21,15 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
           n_jumps=None, save_positions=(False, True), reltol=1e-7, abstol=1e-9, seed=0,
           replay=None, sample_times=None, hist=None, hist_bins=0, precision="fp64",
           device=0, max_attempts=0, max_records=0, no_records=False, tstop_policy=0,
-          ref_quirks=False, xc0=None, xd0=None):
+          ref_quirks=False, xc0=None, xd0=None, xd_transport="int64"):
     """Returns (desc, opts, keepalive).  `info` is the model's pdmp_model_info.
 
     xc0 / xd0 override the problem's (broadcast) initial conditions with per-trajectory
     arrays [trajectories, n_c] / [trajectories, n_d].
-    hist: list of (component, lo, hi)."""
+    hist: list of (component, lo, hi).
+    xd_transport: "int64" (reference layout), "int32" (always exact), "int16", or "auto" = the
+    narrowest width that provably holds |xd0| + (n_jumps - 1) max|nu| (int32 when the model has a
+    Delta, which may move xd arbitrarily)."""
     if n_jumps is None or not np.isfinite(n_jumps):
         raise ValueError("n_jumps must be given and finite for an ensemble solve (the reference "
                          "default Inf64 has no meaning with heavy-tailed jump counts)")
@@ -100,6 +103,12 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
     o.device = int(device)
     o.tstop_policy = int(tstop_policy)
     o.ref_quirks = int(bool(ref_quirks))
+    bound = int(np.max(np.abs(xd), initial=0)) + max(int(n_jumps) - 1, 0) * int(np.max(np.abs(nu), initial=0))
+    if xd_transport == "auto":
+        xd_transport = "int16" if (bound < 32768 and not info.has_delta) else "int32"
+    if xd_transport == "int16" and (bound >= 32768 or info.has_delta):
+        raise ValueError("xd_transport='int16' is not provably exact for this problem (bound %d)" % bound)
+    o.xd_bytes = {"int64": 8, "int32": 4, "int16": 2}[xd_transport]
     return d, o, keep
 
 
@@ -107,7 +116,11 @@ def _arr(ptr, shape, dtype, copy):
     n = int(np.prod(shape))
     if n == 0 or not ptr:
         return np.zeros(shape, dtype=dtype)
-    a = np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).reshape(shape)
+    if isinstance(ptr, int):   # void* field: raw address
+        ptr = C.cast(C.c_void_p(ptr), C.POINTER(C.c_uint8))
+        a = np.ctypeslib.as_array(ptr, shape=(n * np.dtype(dtype).itemsize,)).view(dtype).reshape(shape)
+    else:
+        a = np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).reshape(shape)
     return a.copy() if copy else a
 
 
@@ -121,7 +134,7 @@ def to_numpy(res, *, copy=True, save_positions=(False, True), sample_times=None,
         offsets=_arr(res.offsets, (n + 1,), np.uint64, copy) if records else np.zeros(n + 1, np.uint64),
         time=_arr(res.time, (tot,), np.float64, copy),
         xc=_arr(res.xc, (tot, nc), np.float64, copy),
-        xd=_arr(res.xd, (tot, nd), np.int64, copy),
+        xd=_arr(res.xd, (tot, nd), {8: np.int64, 4: np.int32, 2: np.int16}[int(res.xd_bytes) or 8], copy),
         njumps=_arr(res.njumps, (n,), np.int64, copy),
         nrejected=_arr(res.nrejected, (n,), np.int64, copy),
         status=_arr(res.status, (n,), np.uint8, copy),

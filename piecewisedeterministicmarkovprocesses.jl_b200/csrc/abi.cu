@@ -132,9 +132,11 @@ struct pdmp_ensemble {
     unsigned int* d_segtab = nullptr;
     unsigned long long* d_nrec = nullptr;
     long long* d_njumps = nullptr; long long* d_nrej = nullptr; unsigned char* d_status = nullptr;
-    unsigned long long* d_offsets = nullptr; double* d_time = nullptr; double* d_xc = nullptr; long long* d_xd = nullptr;
+    unsigned long long* d_offsets = nullptr; double* d_time = nullptr; double* d_xc = nullptr; unsigned char* d_xd = nullptr;
+    int xb = 8;  // bytes per saved discrete component (opts.xd_bytes)
     void* d_scan[NS] = {}; size_t scan_bytes = 0;
     unsigned long long csr_cap = 0, pool_blocks = 0;
+    size_t cap_xc0 = 0, cap_xd0 = 0;  // elements allocated for the initial conditions
     size_t n_stats = 0, n_hist = 0;
     // events
     cudaEvent_t ev_fork = nullptr, ev_kbeg = nullptr, ev_kend[NS] = {}, ev_h2d[2] = {nullptr, nullptr},
@@ -143,7 +145,8 @@ struct pdmp_ensemble {
     // host staging (pinned)
     Pinned<unsigned long long> h_offsets, h_hist, h_ctl, h_bound, h_blk;
     Pinned<double> h_time, h_xc, h_stats;
-    Pinned<long long> h_xd, h_njumps, h_nrej;
+    Pinned<long long> h_njumps, h_nrej;
+    Pinned<unsigned char> h_xd;
     Pinned<unsigned char> h_status;
     bool ran = false, host_mode_done = false, host_records = false;
     float ms_kernel = 0, ms_compact = 0;
@@ -212,6 +215,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     if (o->ode != PDMP_ODE_DP5 && o->ode != PDMP_ODE_TSIT5) return fail(PDMP_ERR_INVALID, "ode");
     if (o->precision != PDMP_PREC_FP64) return fail(PDMP_ERR_UNSUPPORTED, "only FP64 is built in this version");
     if (o->rng_mode == PDMP_RNG_REPLAY && (!o->replay_u || !o->replay_stride)) return fail(PDMP_ERR_INVALID, "replay_u");
+    if (o->xd_bytes != 0 && o->xd_bytes != 8 && o->xd_bytes != 4 && o->xd_bytes != 2) return fail(PDMP_ERR_INVALID, "xd_bytes must be 0, 8, 4 or 2");
     if (o->hist_n < 0 || o->hist_n > MAXH) return fail(PDMP_ERR_INVALID, "hist_n must be <= 4");
     if (o->hist_n && o->hist_bins < 1) return fail(PDMP_ERR_INVALID, "hist_bins");
     if (d->n_traj > 0xfffffff0ull) return fail(PDMP_ERR_INVALID, "n_traj per call must be < 2^32");
@@ -222,6 +226,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     auto* e = new pdmp_ensemble();
     std::unique_ptr<pdmp_ensemble> guard(e);
     e->device = o->device; e->m = &m; e->o = *o; e->n = d->n_traj;
+    e->xb = o->xd_bytes ? o->xd_bytes : 8;
     for (auto& st : e->cs) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
     for (cudaEvent_t* ev : {&e->ev_kbeg, &e->ev_h2d[0], &e->ev_h2d[1], &e->ev_d2h[0], &e->ev_d2h[1]}) CK(cudaEventCreate(ev));
@@ -270,8 +275,10 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
 
     // inputs
     const size_t nxc = (size_t)(d->xc0_per_traj ? n : 1) * NC, nxd = (size_t)(d->xd0_per_traj ? n : 1) * ND;
-    CK(cudaMalloc(&e->d_xc0, std::max<size_t>(n, 1) * NC * sizeof(double)));
-    CK(cudaMalloc(&e->d_xd0, std::max<size_t>(n, 1) * ND * sizeof(long long)));
+    // broadcast initial conditions take one entry; upload_ics grows the buffers on demand
+    e->cap_xc0 = std::max<size_t>(nxc, NC); e->cap_xd0 = std::max<size_t>(nxd, ND);
+    CK(cudaMalloc(&e->d_xc0, e->cap_xc0 * sizeof(double)));
+    CK(cudaMalloc(&e->d_xd0, e->cap_xd0 * sizeof(long long)));
     CK(cudaMemcpyAsync(e->d_xc0, d->xc0, nxc * sizeof(double), cudaMemcpyHostToDevice, s0));
     CK(cudaMemcpyAsync(e->d_xd0, d->xd0, nxd * sizeof(long long), cudaMemcpyHostToDevice, s0));
     P.xc0 = e->d_xc0; P.xd0 = e->d_xd0;
@@ -325,7 +332,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         const unsigned long long maxrec = max_records_per_traj(*o);
         P.table_w = table_width(maxrec);
         const size_t rec_bytes = (size_t)m.rec_words * 8;
-        const size_t csr_bytes = (size_t)8 * (1 + NC + ND);
+        const size_t csr_bytes = (size_t)8 * (1 + NC) + (size_t)e->xb * ND;
         const unsigned long long per_traj_worst = pool_records_for(maxrec);
         const unsigned long long worst = n * per_traj_worst;
         int npools = std::min(NS, e->n_chunks);
@@ -370,19 +377,53 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         CK(cudaMemsetAsync(e->d_offsets, 0, sizeof(unsigned long long), s0));
         CK(cudaMalloc(&e->d_time, std::max<size_t>(e->csr_cap, 1) * sizeof(double)));
         CK(cudaMalloc(&e->d_xc, std::max<size_t>(e->csr_cap * NC, 1) * sizeof(double)));
-        CK(cudaMalloc(&e->d_xd, std::max<size_t>(e->csr_cap * ND, 1) * sizeof(long long)));
+        CK(cudaMalloc(&e->d_xd, std::max<size_t>(e->csr_cap * ND, 1) * e->xb));
         P.seg_table = e->d_segtab; P.pool_blocks = e->pool_blocks;
         CK(cub::DeviceScan::ExclusiveScan(nullptr, e->scan_bytes, e->d_nrec, e->d_offsets, AddULL(),
                                           cub::FutureValue<unsigned long long>(e->d_offsets), (long long)n, s0));
         for (int q = 0; q < std::min(NS, e->n_chunks); ++q) CK(cudaMalloc(&e->d_scan[q], std::max<size_t>(e->scan_bytes, 16)));
     } else {
         P.table_w = 1; P.pool_blocks = 0;
+        e->shared_pool = true;  // nothing to compact or stream: resident runs are one persistent kernel
     }
 
     // persistent launch shape: resident CTAs per SM x SM count, capped by the work of a chunk
     int bps = 0, sms = 0;
-    CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, e->smem, &bps));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+    {
+        // kernel flavour: the slot-pool kernel (every warp owns `sw` > 32 trajectory slots in shared
+        // memory and batches converged RK / jump / init phases) unless the model has no flow to
+        // integrate between candidates (then every lane is always at a candidate: nothing to batch)
+        const char* ek = std::getenv("PDMP_KERNEL");
+        const bool want_slots = !(o->algorithm == PDMP_ALG_REJECTION && m.zero_flow) && !(ek && std::atoi(ek) == 1);
+        const size_t stats_b = (e->smem + 15) & ~(size_t)15;
+        const int warps = BLOCK / 32, sb = m.slot_bytes[o->algorithm];
+        auto smem_for = [&](int sw) { return stats_b + (size_t)warps * ((size_t)sw * sb + SLOT_SCRATCH); };
+        int sw = 0;
+        if (want_slots) {
+            const char* es = std::getenv("PDMP_SW");
+            if (es) sw = std::min(64, std::max(34, std::atoi(es) & ~1));
+            else {
+                int ref = 0;
+                CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, true, smem_for(40), &ref));
+                for (int c : {64, 60, 56, 52, 48, 44, 40}) {
+                    int b = 0;
+                    if (smem_for(c) > 227 * 1024) continue;
+                    CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, true, smem_for(c), &b));
+                    if (b >= ref && b >= 1) { sw = c; break; }
+                }
+                if (!sw) sw = 40;
+            }
+            const char* ej = std::getenv("PDMP_JB");
+            const char* ei = std::getenv("PDMP_IB");
+            P.sw = sw;
+            P.jb = ej ? std::max(1, std::atoi(ej)) : std::min(32, std::max(20, sw - 32));
+            P.ib = ei ? std::max(1, std::atoi(ei)) : 8;
+            P.stats_smem_bytes = (int)stats_b;
+            e->smem = smem_for(sw);
+        }
+        CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, sw > 0, e->smem, &bps));
+    }
     if (bps < 1) return fail(PDMP_ERR_CUDA, "kernel does not fit on an SM");
     e->grid = std::max(1, bps * sms);
     CK(cudaStreamSynchronize(s0));  // inputs are borrowed only for the duration of the call
@@ -394,11 +435,25 @@ static int upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc0_per_traj,
                       cudaStream_t st) {
     const int NC = e->m->info.n_c, ND = e->m->info.n_d;
     if (xc0) {
-        CK(cudaMemcpyAsync(e->d_xc0, xc0, (size_t)(xc0_per_traj ? e->n : 1) * NC * sizeof(double), cudaMemcpyHostToDevice, st));
+        const size_t cnt = (size_t)(xc0_per_traj ? e->n : 1) * NC;
+        if (cnt > e->cap_xc0) {
+            CK(cudaStreamSynchronize(st));
+            CK(cudaFree(e->d_xc0)); e->d_xc0 = nullptr; e->cap_xc0 = 0;
+            CK(cudaMalloc(&e->d_xc0, cnt * sizeof(double)));
+            e->cap_xc0 = cnt; e->P.xc0 = e->d_xc0;
+        }
+        CK(cudaMemcpyAsync(e->d_xc0, xc0, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
         e->P.xc0_per_traj = xc0_per_traj;
     }
     if (xd0) {
-        CK(cudaMemcpyAsync(e->d_xd0, xd0, (size_t)(xd0_per_traj ? e->n : 1) * ND * sizeof(long long), cudaMemcpyHostToDevice, st));
+        const size_t cnt = (size_t)(xd0_per_traj ? e->n : 1) * ND;
+        if (cnt > e->cap_xd0) {
+            CK(cudaStreamSynchronize(st));
+            CK(cudaFree(e->d_xd0)); e->d_xd0 = nullptr; e->cap_xd0 = 0;
+            CK(cudaMalloc(&e->d_xd0, cnt * sizeof(long long)));
+            e->cap_xd0 = cnt; e->P.xd0 = e->d_xd0;
+        }
+        CK(cudaMemcpyAsync(e->d_xd0, xd0, cnt * sizeof(long long), cudaMemcpyHostToDevice, st));
         e->P.xd0_per_traj = xd0_per_traj;
     }
     return PDMP_OK;
@@ -430,7 +485,7 @@ static int queue_chunk_d2h(pdmp_ensemble* e, int k, bool fetch_records) {
         if (r1 > r0) {
             CK(cudaMemcpyAsync(e->h_time.p + r0, e->d_time + r0, (r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(e->h_xc.p + r0 * NC, e->d_xc + r0 * NC, (r1 - r0) * NC * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(e->h_xd.p + r0 * ND, e->d_xd + r0 * ND, (r1 - r0) * ND * sizeof(long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(e->h_xd.p + r0 * ND * e->xb, e->d_xd + r0 * ND * e->xb, (r1 - r0) * ND * e->xb, cudaMemcpyDeviceToHost, st));
         }
     }
     return PDMP_OK;
@@ -448,7 +503,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
         CK(e->h_njumps.reserve(e->n)); CK(e->h_nrej.reserve(e->n)); CK(e->h_status.reserve(e->n));
         if (fetch_records && e->records) {
             CK(e->h_offsets.reserve(e->n + 1)); CK(e->h_time.reserve_exact(e->csr_cap));
-            CK(e->h_xc.reserve_exact(e->csr_cap * NC)); CK(e->h_xd.reserve_exact(e->csr_cap * ND));
+            CK(e->h_xc.reserve_exact(e->csr_cap * NC)); CK(e->h_xd.reserve_exact(e->csr_cap * ND * e->xb));
         }
     }
     CK(e->h_bound.reserve(e->n_chunks + 1)); CK(e->h_blk.reserve(e->n_chunks)); CK(e->h_ctl.reserve(CTL_N));
@@ -481,7 +536,8 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
         Pk.seg_table = e->d_segtab ? e->d_segtab + a * Pk.table_w : nullptr;
         Pk.nrec += a; Pk.njumps += a; Pk.nrejected += a; Pk.status += a;
         if (k >= NS) CK(cudaMemsetAsync(e->d_ctl + 2 * q, 0, 2 * sizeof(unsigned long long), st));
-        const int grid = (int)std::min<unsigned long long>(e->grid, (Pk.n_traj + BLOCK - 1) / BLOCK);
+        const unsigned long long per_cta = Pk.sw > 0 ? (unsigned long long)(BLOCK / 32) * Pk.sw : BLOCK;
+        const int grid = (int)std::min<unsigned long long>(e->grid, (Pk.n_traj + per_cta - 1) / per_cta);
         CK(e->m->launch(e->o.algorithm, e->o.ode, e->records, e->stats, Pk, std::max(grid, 1), e->smem, st));
         CK(cudaEventRecord(e->ev_kend[q], st));
         if (e->records && k > 0) CK(cudaStreamWaitEvent(st, e->ev_base[k - 1], 0));  // offsets[a] (start of this chunk) is final
@@ -493,7 +549,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
             chunk_close_kernel<<<1, 32, 0, st>>>(e->d_nrec + a, e->d_offsets + a, b - a, Pk.blk_cursor, e->d_blkhist + k);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e->ev_base[k], st));
-            CK(e->m->compact(Pk, e->d_offsets + a, e->d_time, e->d_xc, e->d_xd, st));
+            CK(e->m->compact(Pk, e->d_offsets + a, e->d_time, e->d_xc, e->d_xd, e->xb, st));
             CK(cudaMemcpyAsync(e->h_bound.p + k + 1, e->d_offsets + b, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         } else {
             chunk_close_kernel<<<1, 32, 0, st>>>(nullptr, nullptr, 0, Pk.blk_cursor, e->d_blkhist + k);
@@ -545,7 +601,7 @@ static int fill_counters(pdmp_ensemble* e, pdmp_result* r) {
     r->total_candidates = e->h_ctl.p[CTL_CT + CT_CANDS];
     r->kernel_ms = e->ms_kernel; r->compact_ms = e->ms_compact;
     r->n_sample_times = e->P.n_sample; r->n_comp = e->P.n_comp; r->hist_n = e->P.hist_n; r->hist_bins = e->P.hist_bins;
-    r->n_c = e->m->info.n_c; r->n_d = e->m->info.n_d;
+    r->n_c = e->m->info.n_c; r->n_d = e->m->info.n_d; r->xd_bytes = e->xb;
     if (e->records && e->n) {
         unsigned long long total = 0;
         CK(cudaMemcpy(&total, e->d_offsets + e->n, sizeof(total), cudaMemcpyDeviceToHost));
@@ -581,7 +637,7 @@ static int fill_views(pdmp_ensemble* e, bool recs, pdmp_result* r) {
     r->stat_sumsq = e->h_stats.p ? e->h_stats.p + 2 * (e->n_stats / 3) : nullptr;
     r->hist = (uint64_t*)e->h_hist.p;
     if (recs) {
-        r->offsets = (uint64_t*)e->h_offsets.p; r->time = e->h_time.p; r->xc = e->h_xc.p; r->xd = (int64_t*)e->h_xd.p;
+        r->offsets = (uint64_t*)e->h_offsets.p; r->time = e->h_time.p; r->xc = e->h_xc.p; r->xd = e->h_xd.p;
     }
     if (pool_overflowed(e))
         return fail(PDMP_ERR_CAPACITY, "record pool exhausted: about " + std::to_string(r->records_needed) +
@@ -626,12 +682,12 @@ int32_t pdmp_ensemble_fetch(pdmp_ensemble* e, int32_t fetch_records, pdmp_result
     const size_t total = recs ? (size_t)r->total_records : 0;
     if (recs) {
         CK(e->h_offsets.reserve(n + 1)); CK(e->h_time.reserve(total)); CK(e->h_xc.reserve(total * NC));
-        CK(e->h_xd.reserve(total * ND));
+        CK(e->h_xd.reserve(total * ND * e->xb));
         CK(cudaMemcpyAsync(e->h_offsets.p, e->d_offsets, (n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         if (total) {
             CK(cudaMemcpyAsync(e->h_time.p, e->d_time, total * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(e->h_xc.p, e->d_xc, total * NC * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(e->h_xd.p, e->d_xd, total * ND * sizeof(long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(e->h_xd.p, e->d_xd, total * ND * e->xb, cudaMemcpyDeviceToHost, st));
         }
     }
     CK(cudaEventRecord(e->ev_d2h[1], st));

@@ -86,7 +86,7 @@ class EnsembleResult:
     offsets: np.ndarray            # [n_traj+1] uint64
     time: np.ndarray               # [total]
     xc: np.ndarray                 # [total, n_c]
-    xd: np.ndarray                 # [total, n_d] int64
+    xd: np.ndarray                 # [total, n_d] int64 (int32 / int16 under a narrow xd_transport)
     njumps: np.ndarray             # [n_traj] int64
     nrejected: np.ndarray          # [n_traj] int64
     status: np.ndarray             # [n_traj] uint8
@@ -105,7 +105,7 @@ class EnsembleResult:
 
     def __getitem__(self, i) -> PDMPResult:
         a, b = int(self.offsets[i]), int(self.offsets[i + 1])
-        return PDMPResult(self.time[a:b], self.xc[a:b].T, self.xd[a:b].T, np.empty(0),
+        return PDMPResult(self.time[a:b], self.xc[a:b].T, self.xd[a:b].T.astype(np.int64, copy=False), np.empty(0),
                           self.save_positions, int(self.njumps[i]), int(self.nrejected[i]),
                           int(self.status[i]))
 

@@ -1,0 +1,197 @@
+#!/usr/bin/env python
+"""Runs BASELINE.json's configs C1..C5 at their full sizes on the GPU(s) and prints one JSON line
+per config: throughput, FP64 roofline fraction, status histogram, plus the parity checks the north
+star asks for "in the same run" (replay: 10^3 trajectories per model against the oracle; Philox:
+ensemble moments against a CPU ensemble within 99 % confidence intervals).
+
+    python scripts/run_configs.py [--only C3] [--scale 1.0]
+    python -m torch.distributed.run --nproc-per-node 8 ... scripts/run_configs.py     (sharded)
+
+bench.py is the headline (C2) benchmark; this script is the evidence for the other configs
+(profiles/r1_configs_*.jsonl).  The oracle is used here only as the checker.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import numpy as np
+
+FLOPS = {"tcp": 180.0, "tcp2d": 282.0, "morris_lecar": 354.0, "sir_rejection": 84.0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--scale", type=float, default=1.0, help="scales the ensemble sizes (for quick runs)")
+    ap.add_argument("--no-parity", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import pdmp_b200 as P
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peak = P.fp64_peak_tflops(local)
+
+    def emit(d):
+        if rank == 0:
+            print(json.dumps(d), flush=True)
+
+    def gather_sum(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        return t.tolist()
+
+    def gather_max(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def throughput(name, model, alg, n_total, reps=3, **kw):
+        """Resident ensemble run of `n_total` trajectories sharded over the ranks."""
+        off, cnt = P.distributed.shard_range(n_total, rank, world)
+        pb = kw.pop("problem")
+        ens = P.Ensemble(pb, alg, trajectories=cnt, traj_id_offset=off, device=local, **kw)
+        ens.run(seed=100)            # warm-up
+        ens.counters()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        best = None
+        for r in range(reps):
+            t0 = time.perf_counter()
+            ens.run(seed=r)
+            if world > 1 and kw.get("sample_times") is not None:
+                P.distributed.allreduce_stats_device(ens, dev)
+            c = ens.counters()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            step_ms = c["kernel_ms"] + c["compact_ms"]
+            if best is None or step_ms < best[0]:
+                best = (step_ms, c, wall)
+        step_ms, c, wall = best
+        res = ens.fetch(records=False)
+        hist = res.status_histogram()
+        tot = gather_sum([c["total_jumps"], c["rk_attempts"], c["total_candidates"], c["total_records"], cnt])
+        ms = gather_max(step_ms)
+        kms = gather_max(c["kernel_ms"])
+        sh = gather_sum([hist.get(k, 0) for k in P._abi.STATUS_NAMES])
+        ach = tot[1] * FLOPS[model] / (kms * 1e-3) / 1e12 / world
+        out = {"config": name, "model": model, "n_gpus": world, "trajectories": int(tot[4]),
+               "jumps_per_sec": tot[0] / (ms * 1e-3), "trajectories_per_sec": tot[4] / (ms * 1e-3),
+               "candidates_per_sec": tot[2] / (ms * 1e-3),
+               "ms_step_max_over_ranks": ms, "kernel_ms": kms, "jumps": int(tot[0]), "rk_attempts": int(tot[1]),
+               "records": int(tot[3]), "status": {k: int(v) for k, v in zip(P._abi.STATUS_NAMES, sh) if v},
+               "fp64_roofline": {"achieved_tflops_per_gpu": ach, "peak_tflops": peak, "frac": ach / peak,
+                                 "flops_per_attempt": FLOPS[model]},
+               "wall_s_incl_sync": wall}
+        ens.close()
+        return out, res
+
+    S = args.scale
+    want = lambda c: (not args.only) or c in args.only.split(",")
+
+    # ---- C1: examples/tcp.jl single trajectory, replay, vs the closed form -------------------
+    if want("C1") and rank == 0:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "closed_forms.npz"))
+        pb = P.models.problem("tcp")
+        out = {"config": "C1", "model": "tcp"}
+        for ode in ("dp5", "tsit5"):
+            r = P.solve(pb, P.CHVGPU("tcp", ode=ode), n_jumps=10, replay=g["tcp10_u"])
+            r2 = P.solve(pb, P.CHVGPU("tcp", ode=ode), n_jumps=700, replay=g["tcp700_u"], reltol=1e-10, abstol=1e-18)
+            out[ode] = {"max_abs_dt_nj10_default_tol": float(np.max(np.abs(r.time - g["tcp10_t"]))),
+                        "max_rel_dt_nj700_tol1e-10": float(np.max(np.abs(r2.time - g["tcp700_t"]) / np.maximum(g["tcp700_t"], 1))),
+                        "xd_bit_exact": bool(np.array_equal(r2.xd[:, 0], g["tcp700_xd"]))}
+        emit(out)
+
+    # ---- C2 is bench.py ------------------------------------------------------------------------
+    # ---- C3: Morris-Lecar CHV, 1e6 trajectories -------------------------------------------------
+    if want("C3"):
+        n = int(1_000_000 * S)
+        out, _ = throughput("C3", "morris_lecar", P.CHVGPU("morris_lecar"), n, problem=P.models.problem("morris_lecar"),
+                            n_jumps=2200, max_records=int(n / world * 760) + 4096, sample_times=[87.5, 175.0, 262.5, 350.0])
+        emit(out)
+    # ---- C4: SIR rejection, 1e7 trajectories ----------------------------------------------------
+    if want("C4"):
+        n = int(10_000_000 * S)
+        out, _ = throughput("C4", "sir_rejection", P.RejectionGPU("sir_rejection"), n, problem=P.models.problem("sir_rejection"),
+                            n_jumps=1000, max_records=int(n / world * 200) + 4096, sample_times=[50.0, 100.0, 150.0])
+        out["note"] = "BOUND_VIOLATED trajectories are the reference's AssertionError (src/rejectiondiffeq.jl:33): the example's bound parms[1]+3.5 is violable (SURVEY finding 0.5)"
+        emit(out)
+    # ---- C5: tcp2d, 1e9 trajectories sharded, statistics + histograms only ---------------------
+    if want("C5"):
+        n = int(1_000_000_000 * S)
+        st = list(10.0 * np.arange(1, 17) / 16)
+        out, res = throughput("C5", "tcp2d", P.CHVGPU("tcp2d"), n, reps=2, problem=P.models.problem("tcp2d", tspan=(0.0, 10.0)),
+                              n_jumps=2000, no_records=True, sample_times=st, hist=[(0, 0.0, 4.0), (1, 0.0, 4.0)], hist_bins=256)
+        if world > 1:
+            res = P.distributed.allreduce_stats_host(res)
+        out["mean_xc_at_tf"] = res.mean()[-1, :2].tolist()
+        out["var_xc_at_tf"] = res.var()[-1, :2].tolist()
+        out["count_at_tf"] = float(res.stat_count[-1, 0])
+        out["hist_total"] = int(res.hist.sum())
+        emit(out)
+
+    # ---- parity in the same run ------------------------------------------------------------------
+    if not args.no_parity and rank == 0 and (want("PARITY") or not args.only):
+        import oracle as orc
+        rng = np.random.default_rng(7)
+        cases = [("tcp", "chv", 200.0, 60, 128), ("tcp2d", "chv", 10.0, 200, 512), ("morris_lecar", "chv", 20.0, 200, 512),
+                 ("sir_rejection", "rejection", 150.0, 1000, 4096), ("pdmp_stiff", "chv", 1e5, 40, 96),
+                 ("tcp_rejection", "rejection", 1e5, 40, 512)]
+        for model, alg, tf, nj, nu_ in cases:
+            pb = P.models.problem(model); pb.tspan[1] = tf
+            U = np.clip(rng.random((1000, nu_)), 2.0 ** -53, 1 - 2.0 ** -53)
+            A = P.CHVGPU(model) if alg == "chv" else P.RejectionGPU(model)
+            kw = dict(trajectories=1000, n_jumps=nj, replay=U, reltol=1e-10, abstol=1e-13)
+            g = P.solve(pb, A, **kw)
+            c = orc.solve(pb, model, algorithm=alg, ode="dp5", **kw)
+            same = bool(np.array_equal(g.offsets, c.offsets) and np.array_equal(g.xd, c.xd) and
+                        np.array_equal(g.njumps, c.njumps) and np.array_equal(g.nrejected, c.nrejected) and
+                        np.array_equal(g.status, c.status))
+            et = float(np.max(np.abs(g.time - c.time) / np.maximum(np.abs(c.time), 1.0))) if same else None
+            ex = float(np.max(np.abs(g.xc - c.xc) / np.maximum(np.abs(c.xc), 1.0))) if same else None
+            emit({"parity": "replay", "model": model, "alg": alg, "trajectories": 1000, "records": int(len(g.time)),
+                  "discrete_bit_exact": same, "max_rel_err_time": et, "max_rel_err_xc": ex, "tolerance": 1e-8})
+        # Philox: GPU 1e7 vs CPU oracle 1e5 (TCP C2 shape), 99 % CI with Bonferroni over T x C tests
+        pb = P.models.problem("tcp", tspan=(0.0, 200.0))
+        st = [50.0, 100.0, 150.0, 200.0]
+        ng, ncpu = int(10_000_000 * S), int(max(100_000 * S, 20_000))
+        g = P.solve(pb, P.CHVGPU("tcp"), trajectories=ng, n_jumps=1000, seed=31, sample_times=st, no_records=True)
+        c = orc.solve(pb, "tcp", algorithm="chv", ode="tsit5", trajectories=ncpu, n_jumps=1000, seed=32, sample_times=st,
+                      no_records=True)
+        from scipy import stats as sst
+        # batch-free CI: var of the mean from sumsq; var of the variance from a normal-theory bound x3 (heavy tails)
+        comps = [0, 1]
+        m = len(st) * len(comps)
+        z = float(sst.norm.ppf(1 - 0.01 / (2 * m)))
+        rows = []
+        for ti in range(len(st)):
+            for ci in comps:
+                n1, n2 = g.stat_count[ti, ci], c.stat_count[ti, ci]
+                m1, m2 = g.mean()[ti, ci], c.mean()[ti, ci]
+                v1, v2 = g.var()[ti, ci], c.var()[ti, ci]
+                se = float(np.sqrt(v1 / n1 + v2 / n2))
+                rows.append({"t": st[ti], "comp": ci, "gpu_mean": float(m1), "cpu_mean": float(m2), "z_mean": float(abs(m1 - m2) / se),
+                             "gpu_var": float(v1), "cpu_var": float(v2), "n_gpu": float(n1), "n_cpu": float(n2)})
+        emit({"parity": "philox_moments", "model": "tcp", "gpu_trajectories": ng, "cpu_trajectories": ncpu, "z_crit_99_bonferroni": z,
+              "all_means_within_ci": bool(all(r["z_mean"] < z for r in rows)), "rows": rows,
+              "note": "count < n because trajectories stopped by the n_jumps cap before a sample time are not sampled there"})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -400,3 +400,26 @@ def test_chunked_pipeline_matches_single_chunk(G, monkeypatch):
 def test_fp64_peak_probe(G):
     tf = G.fp64_peak_tflops()
     assert 10.0 < tf < 80.0, tf
+
+
+def test_xd_transport_widths(G):
+    # narrow transport of the saved discrete states is lossless: int64 == int32 == int16 results
+    pb = G.models.problem("tcp", tspan=(0.0, 200.0))
+    kw = dict(trajectories=5000, n_jumps=300, seed=3)
+    r8 = G.solve(pb, G.CHVGPU("tcp"), **kw)
+    r4 = G.solve(pb, G.CHVGPU("tcp"), xd_transport="int32", **kw)
+    r2 = G.solve(pb, G.CHVGPU("tcp"), xd_transport="auto", **kw)
+    assert r8.xd.dtype == np.int64 and r4.xd.dtype == np.int32 and r2.xd.dtype == np.int16
+    for r in (r4, r2):
+        assert np.array_equal(r.xd, r8.xd) and np.array_equal(r.time, r8.time) and np.array_equal(r.xc, r8.xc)
+        assert np.array_equal(r.offsets, r8.offsets)
+    assert r2[7].xd.dtype == np.int64 and np.array_equal(r2[7].xd, r8[7].xd)     # widened per trajectory
+    ml = G.models.problem("morris_lecar")
+    a = G.solve(ml, G.CHVGPU("morris_lecar"), trajectories=500, n_jumps=400, seed=1)
+    b = G.solve(ml, G.CHVGPU("morris_lecar"), trajectories=500, n_jumps=400, seed=1, xd_transport="auto")
+    assert b.xd.dtype == np.int16 and np.array_equal(a.xd, b.xd)
+    with pytest.raises(ValueError):   # 40000 jumps could overflow int16: refused on the host
+        G.solve(pb, G.CHVGPU("tcp"), trajectories=4, n_jumps=40000, xd_transport="int16")
+    ev = G.models.problem("neuron_eva")   # a Delta may move xd arbitrarily: auto stays at int32
+    c = G.solve(ev, G.RejectionGPU("neuron_eva"), trajectories=64, n_jumps=50, seed=2, xd_transport="auto")
+    assert c.xd.dtype == np.int32
