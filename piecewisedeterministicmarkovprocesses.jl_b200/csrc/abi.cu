@@ -390,40 +390,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     // persistent launch shape: resident CTAs per SM x SM count, capped by the work of a chunk
     int bps = 0, sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
-    {
-        // kernel flavour: the slot-pool kernel (every warp owns `sw` > 32 trajectory slots in shared
-        // memory and batches converged RK / jump / init phases) unless the model has no flow to
-        // integrate between candidates (then every lane is always at a candidate: nothing to batch)
-        const char* ek = std::getenv("PDMP_KERNEL");
-        const bool want_slots = !(o->algorithm == PDMP_ALG_REJECTION && m.zero_flow) && !(ek && std::atoi(ek) == 1);
-        const size_t stats_b = (e->smem + 15) & ~(size_t)15;
-        const int warps = BLOCK / 32, sb = m.slot_bytes[o->algorithm];
-        auto smem_for = [&](int sw) { return stats_b + (size_t)warps * ((size_t)sw * sb + SLOT_SCRATCH); };
-        int sw = 0;
-        if (want_slots) {
-            const char* es = std::getenv("PDMP_SW");
-            if (es) sw = std::min(64, std::max(34, std::atoi(es) & ~1));
-            else {
-                int ref = 0;
-                CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, true, smem_for(40), &ref));
-                for (int c : {64, 60, 56, 52, 48, 44, 40}) {
-                    int b = 0;
-                    if (smem_for(c) > 227 * 1024) continue;
-                    CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, true, smem_for(c), &b));
-                    if (b >= ref && b >= 1) { sw = c; break; }
-                }
-                if (!sw) sw = 40;
-            }
-            const char* ej = std::getenv("PDMP_JB");
-            const char* ei = std::getenv("PDMP_IB");
-            P.sw = sw;
-            P.jb = ej ? std::max(1, std::atoi(ej)) : std::min(32, std::max(20, sw - 32));
-            P.ib = ei ? std::max(1, std::atoi(ei)) : 8;
-            P.stats_smem_bytes = (int)stats_b;
-            e->smem = smem_for(sw);
-        }
-        CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, sw > 0, e->smem, &bps));
-    }
+    CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, e->smem, &bps));
     if (bps < 1) return fail(PDMP_ERR_CUDA, "kernel does not fit on an SM");
     e->grid = std::max(1, bps * sms);
     CK(cudaStreamSynchronize(s0));  // inputs are borrowed only for the duration of the call
@@ -536,8 +503,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
         Pk.seg_table = e->d_segtab ? e->d_segtab + a * Pk.table_w : nullptr;
         Pk.nrec += a; Pk.njumps += a; Pk.nrejected += a; Pk.status += a;
         if (k >= NS) CK(cudaMemsetAsync(e->d_ctl + 2 * q, 0, 2 * sizeof(unsigned long long), st));
-        const unsigned long long per_cta = Pk.sw > 0 ? (unsigned long long)(BLOCK / 32) * Pk.sw : BLOCK;
-        const int grid = (int)std::min<unsigned long long>(e->grid, (Pk.n_traj + per_cta - 1) / per_cta);
+        const int grid = (int)std::min<unsigned long long>(e->grid, (Pk.n_traj + BLOCK - 1) / BLOCK);
         CK(e->m->launch(e->o.algorithm, e->o.ode, e->records, e->stats, Pk, std::max(grid, 1), e->smem, st));
         CK(cudaEventRecord(e->ev_kend[q], st));
         if (e->records && k > 0) CK(cudaStreamWaitEvent(st, e->ev_base[k - 1], 0));  // offsets[a] (start of this chunk) is final

@@ -40,8 +40,6 @@ struct KParams {
     long long n_jumps, max_attempts;
     int save_pre, save_post, tstop_policy, rng_mode;
     int jump_thresh, refill_thresh;  // phase scheduler: lanes that must wait before JUMP / REFILL run
-    int sw, jb, ib;                  // slot-pool kernel: slots per warp (0: lane-resident kernel), jump / init batch thresholds
-    int stats_smem_bytes;            // bytes of the CTA statistics block in front of the slot pools
     unsigned long long seed;
     const double* replay_u;
     unsigned long long replay_stride;
@@ -262,73 +260,6 @@ struct Traj {
     }
 
 
-    // ---- slot pool I/O (slot-pool kernel) ------------------------------------------------
-    // A warp owns SW trajectory slots in shared memory, one record of SLOT_BYTES per slot: N64
-    // 8-byte words then N32 4-byte words, all at compile-time offsets from the slot pointer.
-    // SLOT_BYTES / 8 is odd, so consecutive slots start in different banks.  The RK phase keeps
-    // only the integrator subset in registers; the jump / init phases load and store everything.
-    enum { F_Y = 0, F_K1 = D, F_S = 2 * D, F_TSTOP, F_H, F_TLAST, F_XS, F_TS = F_XS + NC, F_WSLOT, F_CACHE, F_SIMNJ,
-           F_NFICT, N64 };
-    enum { G_LQ2 = 0, G_XD, G_ATT = G_XD + ND, G_IDX, G_LID, G_NREC, G_SEGL, G_SEGK, G_NEXTS, G_FLAGS, N32 };
-    static constexpr int SLOT_WORDS8 = (N64 + (N32 + 1) / 2) | 1;
-    static constexpr int SLOT_BYTES = 8 * SLOT_WORDS8;
-    PDMP_DEV static double* q64(unsigned char* sp) { return reinterpret_cast<double*>(sp); }
-    PDMP_DEV static unsigned* q32(unsigned char* sp) { return reinterpret_cast<unsigned*>(sp + 8 * N64); }
-
-    PDMP_DEV void load_rk(unsigned char* sp) {
-        const double* a = q64(sp); const unsigned* b = q32(sp);
-#pragma unroll
-        for (int i = 0; i < D; ++i) { y[i] = a[F_Y + i]; k1[i] = a[F_K1 + i]; }
-        s = a[F_S]; tstop = a[F_TSTOP]; h = a[F_H];
-        pi.lq2 = __uint_as_float(b[G_LQ2]);
-#pragma unroll
-        for (int i = 0; i < ND; ++i) xd[i] = (int)b[G_XD + i];
-        attempts = b[G_ATT];
-    }
-    // xd and tstop never change in the RK phase: only the integrator variables go back
-    PDMP_DEV void store_rk(unsigned char* sp) const {
-        double* a = q64(sp); unsigned* b = q32(sp);
-#pragma unroll
-        for (int i = 0; i < D; ++i) { a[F_Y + i] = y[i]; a[F_K1 + i] = k1[i]; }
-        a[F_S] = s; a[F_H] = h;
-        b[G_LQ2] = __float_as_uint(pi.lq2);
-        b[G_ATT] = attempts;
-    }
-    PDMP_DEV void load_full(unsigned char* sp, int& failcode) {
-        load_rk(sp);
-        const double* a = q64(sp); const unsigned* b = q32(sp);
-        tlast = a[F_TLAST]; ts = a[F_TS];
-#pragma unroll
-        for (int i = 0; i < NC; ++i) xs[i] = a[F_XS + i];
-        wslot = (unsigned long long)__double_as_longlong(a[F_WSLOT]);
-        rng.cache = a[F_CACHE];
-        simnj = __double_as_longlong(a[F_SIMNJ]);
-        nfict = __double_as_longlong(a[F_NFICT]);
-        rng.idx = b[G_IDX]; lid = b[G_LID];
-        nrec_stored = b[G_NREC]; seg_left = b[G_SEGL];
-        seg_k = (int)b[G_SEGK]; next_sample = (int)b[G_NEXTS];
-        const unsigned fl = b[G_FLAGS];
-        overflow = fl & 1u; failcode = (int)(fl >> 8);
-    }
-    PDMP_DEV void store_full(unsigned char* sp) const {
-        store_rk(sp);
-        double* a = q64(sp); unsigned* b = q32(sp);
-        a[F_TSTOP] = tstop;
-#pragma unroll
-        for (int i = 0; i < ND; ++i) b[G_XD + i] = (unsigned)xd[i];
-        a[F_TLAST] = tlast; a[F_TS] = ts;
-#pragma unroll
-        for (int i = 0; i < NC; ++i) a[F_XS + i] = xs[i];
-        a[F_WSLOT] = __longlong_as_double((long long)wslot);
-        a[F_CACHE] = rng.cache;
-        a[F_SIMNJ] = __longlong_as_double(simnj);
-        a[F_NFICT] = __longlong_as_double(nfict);
-        b[G_IDX] = rng.idx; b[G_LID] = lid;
-        b[G_NREC] = nrec_stored; b[G_SEGL] = seg_left;
-        b[G_SEGK] = (unsigned)seg_k; b[G_NEXTS] = (unsigned)next_sample;
-        b[G_FLAGS] = overflow ? 1u : 0u;
-    }
-
     // ---- init!(problem) + integrator construction --------------------------------------
     // reference src/problem.jl:150-161, src/chvdiffeq.jl:97-136, src/rejectiondiffeq.jl:91-116
     PDMP_DEV void init(const KParams& P, unsigned idx, bool& exhausted) {
@@ -410,12 +341,29 @@ struct Traj {
     }
 
     // ---- chvjump, reference src/chvdiffeq.jl:24-74, and the tail of the while body :145-157 ----
+    // time of the threshold the trajectory sits on (CHV: the time slot; Rejection: s is time)
+    PDMP_DEV double threshold_time() const { return ALG == PDMP_ALG_CHV ? y[D - 1] : s; }
+    // a fixed sample time lies at or before this threshold: the anchor flow must run first
+    PDMP_DEV bool sample_due(const KParams& P) const {
+        if constexpr (!STATS) return false;
+        return next_sample < P.n_sample && __ldg(P.sample_times + next_sample) <= fmin(threshold_time(), P.tf);
+    }
+    // the sampling part of the threshold section, separable so that the slot-pool kernel can run
+    // it as its own (rare, divergent) pass and keep the jump pass converged; returns a status
+    PDMP_DEV int pre_sample(const KParams& P, double* sstat, unsigned* shist, unsigned& aux) {
+        int fail = PDMP_ST_OK;
+        sample_until(P, sstat, shist, fmin(threshold_time(), P.tf), aux, fail);
+        return fail;
+    }
+
+    template <bool SAMPLED = false>
     PDMP_DEV bool chv_threshold(const KParams& P, double* sstat, unsigned* shist, unsigned& aux,
                                 unsigned& jumps) {
         int fail = PDMP_ST_OK;
         bool ex = false;
         const double tj = y[NC];
-        if (!sample_until(P, sstat, shist, fmin(tj, P.tf), aux, fail)) { finish(P, fail); return true; }
+        if constexpr (!SAMPLED)
+            if (!sample_until(P, sstat, shist, fmin(tj, P.tf), aux, fail)) { finish(P, fail); return true; }
         if (P.save_pre && tj <= P.tf) write_record(P, tj, y);  // :41-48
         double rate[NR];
         M::rates(rate, y, xd, P.parms, tj);  // :51, rates at the PRE-jump state
@@ -450,12 +398,14 @@ struct Traj {
     }
 
     // ---- rejectionjump, reference src/rejectiondiffeq.jl:14-74, and :121-139 ----
+    template <bool SAMPLED = false>
     PDMP_DEV bool rej_candidate(const KParams& P, double* sstat, unsigned* shist, unsigned& aux,
                                 unsigned& jumps) {
         int fail = PDMP_ST_OK;
         bool ex = false;
         const double tc = s;
-        if (!sample_until(P, sstat, shist, fmin(tc, P.tf), aux, fail)) { finish(P, fail); return true; }
+        if constexpr (!SAMPLED)
+            if (!sample_until(P, sstat, shist, fmin(tc, P.tf), aux, fail)) { finish(P, fail); return true; }
         double rate[NR];
         M::rates(rate, y, xd, P.parms, tc);
         double tot = rate[0];
@@ -566,11 +516,21 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
         const int n_live = n_run + n_wait;
         if (n_wait && (n_run == 0 || n_wait >= min(P.jump_thresh, (n_live + 1) >> 1))) {
             // ---- JUMP ----
+            // sampling pass first: the few lanes whose threshold lies beyond a fixed sample time flow
+            // their anchor there; a block of its own, so that the warp is converged again for the jump pass
+            int fc = 0;
+            if constexpr (STATS) {
+                const bool due = st == LANE_WAIT && tr.sample_due(P);
+                if (__any_sync(0xffffffffu, due)) {
+                    if (due) fc = tr.pre_sample(P, sstat, shist, c_aux);
+                }
+            }
             if (st == LANE_WAIT) {
                 ++c_cands;
                 bool done;
-                if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, sstat, shist, c_aux, c_jumps);
-                else done = tr.rej_candidate(P, sstat, shist, c_aux, c_jumps);
+                if (fc) { tr.finish(P, fc); done = true; }
+                else if constexpr (ALG == PDMP_ALG_CHV) done = tr.template chv_threshold<true>(P, sstat, shist, c_aux, c_jumps);
+                else done = tr.template rej_candidate<true>(P, sstat, shist, c_aux, c_jumps);
                 if (done) st = LANE_DEAD;
                 else if (NO_FLOW) { tr.s = tr.tstop; }   // F = F_dummy: next candidate directly
                 else st = LANE_RUN;
@@ -646,237 +606,6 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
 
 
 // -----------------------------------------------------------------------------------------
-// Slot-pool kernel.  Every WARP owns SW (<= 64) trajectory slots in shared memory — more
-// trajectories than lanes — and each iteration picks up to 32 slots that need the SAME kind of
-// work, so that all three sections run converged:
-//   JUMP  when >= jb slots wait at their threshold: one slot per lane, full state loaded from the
-//         pool, chvjump / rejectionjump, stored back as READY (or freed when the trajectory ended)
-//   INIT  when >= ib slots are free: new trajectories from the global cursor
-//   RK    otherwise: lanes take READY slots, keep only the integrator variables in registers and
-//         step until they land on their threshold; a lane that lands parks its slot (WAIT) and
-//         immediately takes another READY slot
-// All bookkeeping (three 64-bit slot masks) lives in warp-uniform registers; there is no
-// inter-warp communication and no atomics besides the global work cursor and the record pool.
-// -----------------------------------------------------------------------------------------
-typedef unsigned long long ull_t;
-
-// The k-th lane with want=true receives the k-th set bit of m (or -1); `taken` = the bits handed
-// out (the lowest min(#want, #bits) set bits of m).  tmp: 64 bytes of warp-private scratch; two
-// halves used alternately (`flip`) so that one __syncwarp per call suffices.
-PDMP_DEV int assign_slots(ull_t m, bool want, unsigned lane, unsigned char* tmp, unsigned& flip, ull_t& taken) {
-    const unsigned wmask = __ballot_sync(0xffffffffu, want);
-    const int nw = __popc(wmask);
-    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
-    const int nlo = __popc(lo), nb = nlo + __popc(hi);
-    const int ntake = min(nw, nb);
-    unsigned char* t = tmp + (flip & 32u);
-    flip ^= 32u;
-    const unsigned below = (1u << lane) - 1u;
-    if ((lo >> lane) & 1u) { const int r = __popc(lo & below); if (r < ntake) t[r] = (unsigned char)lane; }
-    if ((hi >> lane) & 1u) { const int r = nlo + __popc(hi & below); if (r < ntake) t[r] = (unsigned char)(32u + lane); }
-    __syncwarp();
-    int slot = -1;
-    taken = 0ull;
-    if (ntake > 0) {
-        const int k = __popc(wmask & below);
-        if (want && k < ntake) slot = t[k];
-        const int last = t[ntake - 1];                       // position of the last bit handed out
-        taken = m & ((2ull << last) - 1ull);                 // all set bits up to and including it
-    }
-    return slot;
-}
-PDMP_DEV ull_t reduce_or64(ull_t x) {
-    const unsigned tlo = __reduce_or_sync(0xffffffffu, (unsigned)x);
-    const unsigned thi = __reduce_or_sync(0xffffffffu, (unsigned)(x >> 32));
-    return ((ull_t)thi << 32) | tlo;
-}
-
-// per-warp scratch behind the slot records: 64 bytes for assign_slots + per-lane work counters
-constexpr int SLOT_SCRATCH = 64 + 32 * (8 + 4 * 4);
-
-template <class M, class Tab, int ALG, bool RECORDS, bool STATS>
-__global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kernel_slots(const __grid_constant__ KParams P) {
-    using T = Traj<M, Tab, ALG, RECORDS, STATS>;
-    constexpr int D = T::D;
-    extern __shared__ double smem[];
-    if (STATS && P.stats_in_smem) {
-        double* sstat = smem;
-        unsigned* shist = reinterpret_cast<unsigned*>(smem + 3 * P.n_sample * P.n_comp);
-        const int nd = 3 * P.n_sample * P.n_comp, nh = P.n_sample * P.hist_n * P.hist_bins;
-        for (int i = threadIdx.x; i < nd; i += BLOCK) sstat[i] = 0.0;
-        for (int i = threadIdx.x; i < nh; i += BLOCK) shist[i] = 0u;
-        __syncthreads();
-    }
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned char* const pool = reinterpret_cast<unsigned char*>(smem) + P.stats_smem_bytes +
-                                (size_t)(threadIdx.x >> 5) * ((size_t)P.sw * T::SLOT_BYTES + SLOT_SCRATCH);
-    auto slot_ptr = [&](int j) { return pool + j * T::SLOT_BYTES; };
-    auto tmp_ptr = [&]() { return pool + P.sw * T::SLOT_BYTES; };
-    // per-lane work counters live in shared memory (they are touched once per batch, not per step)
-    auto ctr64 = [&]() { return reinterpret_cast<unsigned long long*>(tmp_ptr() + 64) + lane; };
-    auto ctr32 = [&](int k) { return reinterpret_cast<unsigned*>(tmp_ptr() + 64 + 32 * 8) + k * 32 + lane; };
-    *ctr64() = 0ull;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) *ctr32(k) = 0u;
-    unsigned flip = 0;
-
-    // slot masks (warp-uniform): free slots stop being tracked once the global cursor is exhausted
-    ull_t m_free = P.sw >= 64 ? ~0ull : ((1ull << P.sw) - 1ull), m_ready = 0ull, m_wait = 0ull;
-    bool exhausted = false;
-
-    for (;;) {
-        const int n_wait = __popcll(m_wait), n_ready = __popcll(m_ready), n_free = __popcll(m_free);
-        // jump as soon as jb slots wait — or half of the live ones, when few are left (the tail)
-        if (n_wait && n_wait >= min(P.jb, (n_wait + n_ready + 1) >> 1)) {
-            // ---- JUMP batch ----
-            ull_t taken;
-            const int j = assign_slots(m_wait, true, lane, tmp_ptr(), flip, taken);
-            m_wait &= ~taken;
-            ull_t b_ready = 0ull, b_free = 0ull;
-            if (j >= 0) {
-                T tr;
-                int fc;
-                bool done;
-                unsigned c_aux = 0, c_jumps = 0;
-                unsigned char* sp = slot_ptr(j);
-                tr.load_full(sp, fc);
-                if (fc) { tr.finish(P, fc); done = true; }
-                else {
-                    double* sstat = smem;
-                    unsigned* shist = reinterpret_cast<unsigned*>(smem + 3 * P.n_sample * P.n_comp);
-                    if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, sstat, shist, c_aux, c_jumps);
-                    else done = tr.rej_candidate(P, sstat, shist, c_aux, c_jumps);
-                    *ctr32(3) += 1u;
-                }
-                if (!done) { tr.store_full(sp); b_ready = 1ull << j; } else b_free = 1ull << j;
-                *ctr32(1) += c_aux; *ctr32(2) += c_jumps;
-            }
-            m_ready |= reduce_or64(b_ready);
-            if (!exhausted) m_free |= reduce_or64(b_free);
-            continue;
-        }
-        if (n_free && (n_free >= P.ib || n_ready == 0)) {
-            // ---- INIT batch ----
-            ull_t taken;
-            const int j = assign_slots(m_free, true, lane, tmp_ptr(), flip, taken);   // lane k takes the k-th free slot
-            m_free &= ~taken;
-            const int cnt = __popcll(taken);
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(P.cursor, (unsigned long long)cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            ull_t b_ready = 0ull, b_free = 0ull;
-            if (j >= 0) {
-                const unsigned long long idx = base + lane;
-                if (idx < P.n_traj) {
-                    T tr;
-                    bool ex = false;
-                    tr.init(P, (unsigned)idx, ex);
-                    if (!(tr.simnj < P.n_jumps)) { tr.finish(P, PDMP_ST_HIT_NJUMPS); b_free = 1ull << j; }
-                    else if (ex) { tr.finish(P, PDMP_ST_REPLAY_EXHAUSTED); b_free = 1ull << j; }
-                    else { tr.store_full(slot_ptr(j)); b_ready = 1ull << j; }
-                }
-            }
-            m_ready |= reduce_or64(b_ready);
-            m_free |= reduce_or64(b_free);
-            if (base + (unsigned long long)cnt >= P.n_traj) { exhausted = true; m_free = 0ull; }
-            continue;
-        }
-        if (n_ready == 0) break;  // nothing waits (else the JUMP batch fired), nothing left to start
-        {
-            // ---- RK block: integrator variables in registers until the lane lands on its threshold ----
-            T tr;
-            ull_t taken;
-            int slot = assign_slots(m_ready, true, lane, tmp_ptr(), flip, taken);
-            m_ready &= ~taken;
-            if (slot >= 0) tr.load_rk(slot_ptr(slot));
-            ull_t my_wait = 0ull;              // slots this lane parked at their threshold
-            int nw = n_wait;                   // warp-uniform count of waiting slots
-            unsigned att = 0, rej = 0;
-            for (;;) {
-                bool lost = false;
-                if (slot >= 0) {
-                    const double hprop = tr.h;
-                    double step = hprop;
-                    bool clipped = false;
-                    const double rem = tr.tstop - tr.s;
-                    if (step >= rem) { step = rem; clipped = true; }
-                    double yn[D], k7[D];
-                    auto rhs = [&](const double* x, double* dx, double t) { tr.field(P, x, dx, t); };
-                    const double e2 = rk_attempt<Tab, D>(rhs, tr.y, tr.k1, tr.s, step, yn, k7, P.reltol, P.abstol);
-                    ++att;
-                    const bool accept = e2 <= (double)D;
-                    double hnext;
-                    int fc = 0;
-                    if (e2 < 1.7976931348623157e308) {
-                        hnext = step * tr.pi.step(e2 * (1.0 / D), accept);
-                    } else {
-                        bool ok = true;
-#pragma unroll
-                        for (int i = 0; i < D; ++i) ok = ok && isfinite(tr.y[i]) && isfinite(tr.k1[i]);
-                        hnext = 0.2 * step;
-                        if (!ok || !(tr.s + hnext > tr.s)) fc = PDMP_ST_NAN;
-                    }
-                    if (!fc && (long long)++tr.attempts > min((long long)0x7fffffff, P.max_attempts)) fc = PDMP_ST_MAX_ATTEMPTS;
-                    if (fc) {
-                        T::q32(slot_ptr(slot))[T::G_FLAGS] |= (unsigned)fc << 8;  // the JUMP batch finishes the trajectory
-                        lost = true;
-                    } else {
-                        if (accept) {
-#pragma unroll
-                            for (int i = 0; i < D; ++i) { tr.y[i] = yn[i]; tr.k1[i] = k7[i]; }
-                            double sn = tr.s + step;
-                            if (clipped || rem - step < 2.220446049250313e-14 * fabs(tr.tstop)) { sn = tr.tstop; lost = true; }
-                            tr.s = sn;
-                            if (clipped && P.tstop_policy == 1) hnext = fmax(hnext, hprop);
-                        } else {
-                            ++rej;
-                        }
-                        tr.h = hnext;
-                    }
-                    if (lost) { tr.store_rk(slot_ptr(slot)); my_wait |= 1ull << slot; slot = -1; }
-                }
-                const unsigned lm = __ballot_sync(0xffffffffu, lost);
-                if (lm) {
-                    nw += __popc(lm);
-                    if (m_ready) {
-                        ull_t tk;
-                        const int ns = assign_slots(m_ready, slot < 0, lane, tmp_ptr(), flip, tk);
-                        m_ready &= ~tk;
-                        if (ns >= 0) { slot = ns; tr.load_rk(slot_ptr(slot)); }
-                    }
-                    const int n_run = __popc(__ballot_sync(0xffffffffu, slot >= 0));
-                    if (n_run == 0 || nw >= min(P.jb, (nw + n_run + __popcll(m_ready) + 1) >> 1)) break;
-                }
-            }
-            if (slot >= 0) tr.store_rk(slot_ptr(slot));
-            m_ready |= reduce_or64(slot >= 0 ? 1ull << slot : 0ull);
-            m_wait |= reduce_or64(my_wait);
-            *ctr64() += att; *ctr32(0) += rej;
-        }
-    }
-
-    // ---- flush counters (warp reduce, one atomic per warp) and CTA statistics ----
-    unsigned long long v[CT_N] = {*ctr64(), *ctr32(0), *ctr32(1), *ctr32(2), *ctr32(3)};
-#pragma unroll
-    for (int k = 0; k < CT_N; ++k) {
-        unsigned long long x = v[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0 && x) atomicAdd(P.counters + k, x);
-    }
-    if (STATS && P.stats_in_smem) {
-        __syncthreads();
-        double* sstat = smem;
-        unsigned* shist = reinterpret_cast<unsigned*>(smem + 3 * P.n_sample * P.n_comp);
-        const int nd = 3 * P.n_sample * P.n_comp, nh = P.n_sample * P.hist_n * P.hist_bins;
-        for (int i = threadIdx.x; i < nd; i += BLOCK)
-            if (sstat[i] != 0.0) atomicAdd(P.stats + i, sstat[i]);
-        for (int i = threadIdx.x; i < nh; i += BLOCK)
-            if (shist[i]) atomicAdd(P.hist + i, (unsigned long long)shist[i]);
-    }
-}
-
-// -----------------------------------------------------------------------------------------
 // Host-visible launcher table entry
 // -----------------------------------------------------------------------------------------
 struct ModelEntry {
@@ -885,10 +614,8 @@ struct ModelEntry {
     // launch(alg, ode, records, stats, P, grid, smem, stream): returns cudaError_t
     cudaError_t (*launch)(int alg, int ode, bool records, bool stats, const KParams& P, int grid, size_t smem,
                           cudaStream_t stream);
-    // occupancy: resident CTAs per SM for that variant (slots: the slot-pool kernel)
-    cudaError_t (*occupancy)(int alg, int ode, bool records, bool stats, bool slots, size_t smem, int* blocks_per_sm);
-    int slot_bytes[2];  // shared-memory bytes of one trajectory slot, per algorithm
-    int zero_flow;
+    // occupancy: resident CTAs per SM for that variant
+    cudaError_t (*occupancy)(int alg, int ode, bool records, bool stats, size_t smem, int* blocks_per_sm);
     // compaction pool -> CSR
     cudaError_t (*compact)(const KParams& P, const unsigned long long* offsets, double* time, double* xc,
                            void* xd, int xd_bytes, cudaStream_t stream);
@@ -944,27 +671,21 @@ __global__ void __launch_bounds__(128, 16) compact_kernel(const KParams P, const
 
 // calls f(kernel function pointer) for the requested variant
 template <class M, class Tab, int ALG, class Fn>
-cudaError_t with_variant(bool records, bool stats, bool slots, Fn&& f) {
-    if (slots) {
-        if (records && stats) return f(ensemble_kernel_slots<M, Tab, ALG, true, true>);
-        if (records) return f(ensemble_kernel_slots<M, Tab, ALG, true, false>);
-        if (stats) return f(ensemble_kernel_slots<M, Tab, ALG, false, true>);
-        return f(ensemble_kernel_slots<M, Tab, ALG, false, false>);
-    }
+cudaError_t with_variant(bool records, bool stats, Fn&& f) {
     if (records && stats) return f(ensemble_kernel<M, Tab, ALG, true, true>);
     if (records) return f(ensemble_kernel<M, Tab, ALG, true, false>);
     if (stats) return f(ensemble_kernel<M, Tab, ALG, false, true>);
     return f(ensemble_kernel<M, Tab, ALG, false, false>);
 }
 template <class M, class Fn>
-cudaError_t with_model_variant(int alg, int ode, bool records, bool stats, bool slots, Fn&& f) {
+cudaError_t with_model_variant(int alg, int ode, bool records, bool stats, Fn&& f) {
     if (alg == PDMP_ALG_CHV) {
-        return ode == PDMP_ODE_TSIT5 ? with_variant<M, TabTsit5, PDMP_ALG_CHV>(records, stats, slots, f)
-                                     : with_variant<M, TabDP5, PDMP_ALG_CHV>(records, stats, slots, f);
+        return ode == PDMP_ODE_TSIT5 ? with_variant<M, TabTsit5, PDMP_ALG_CHV>(records, stats, f)
+                                     : with_variant<M, TabDP5, PDMP_ALG_CHV>(records, stats, f);
     }
     if constexpr (M::HAS_BOUND) {
-        return ode == PDMP_ODE_TSIT5 ? with_variant<M, TabTsit5, PDMP_ALG_REJECTION>(records, stats, slots, f)
-                                     : with_variant<M, TabDP5, PDMP_ALG_REJECTION>(records, stats, slots, f);
+        return ode == PDMP_ODE_TSIT5 ? with_variant<M, TabTsit5, PDMP_ALG_REJECTION>(records, stats, f)
+                                     : with_variant<M, TabDP5, PDMP_ALG_REJECTION>(records, stats, f);
     }
     return cudaErrorInvalidValue;
 }
@@ -972,7 +693,7 @@ cudaError_t with_model_variant(int alg, int ode, bool records, bool stats, bool 
 template <class M>
 cudaError_t model_launch(int alg, int ode, bool records, bool stats, const KParams& P, int grid, size_t smem,
                          cudaStream_t st) {
-    return with_model_variant<M>(alg, ode, records, stats, P.sw > 0, [&](auto kern) {
+    return with_model_variant<M>(alg, ode, records, stats, [&](auto kern) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -982,8 +703,8 @@ cudaError_t model_launch(int alg, int ode, bool records, bool stats, const KPara
     });
 }
 template <class M>
-cudaError_t model_occupancy(int alg, int ode, bool records, bool stats, bool slots, size_t smem, int* out) {
-    return with_model_variant<M>(alg, ode, records, stats, slots, [&](auto kern) {
+cudaError_t model_occupancy(int alg, int ode, bool records, bool stats, size_t smem, int* out) {
+    return with_model_variant<M>(alg, ode, records, stats, [&](auto kern) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -1013,9 +734,6 @@ ModelEntry make_entry(int id) {
     e.info.has_bound = M::HAS_BOUND; e.info.has_delta = M::HAS_DELTA; e.info.zero_flow = M::ZERO_FLOW;
     for (int i = 0; M::NAME[i] && i < 31; ++i) e.info.name[i] = M::NAME[i];
     e.rec_words = RecLayout<M>::WORDS;
-    e.slot_bytes[PDMP_ALG_CHV] = Traj<M, TabDP5, PDMP_ALG_CHV, false, false>::SLOT_BYTES;
-    e.slot_bytes[PDMP_ALG_REJECTION] = Traj<M, TabDP5, PDMP_ALG_REJECTION, false, false>::SLOT_BYTES;
-    e.zero_flow = M::ZERO_FLOW;
     e.launch = &model_launch<M>;
     e.occupancy = &model_occupancy<M>;
     e.compact = &model_compact<M>;
