@@ -113,6 +113,25 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this rank's host threads (and therefore its first-touch pinned staging) to the CPUs NVML
+    reports as local to the GPU, so that 8 ranks streaming results over PCIe do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def host_ics(n, pinned=True):
     import torch
     u = np.random.default_rng(2024).random(n)
@@ -185,6 +204,7 @@ def run_gpu(args):
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.traj
@@ -311,6 +331,8 @@ def run_gpu(args):
                                 "note": "compact_ms also contains the offsets scan"},
             "clocks": clk,
         }
+        if numa:
+            line["host_affinity_rank0"] = f"{len(numa)} CPUs local to GPU {local} (NVML)"
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.cpu_sample).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}

@@ -222,7 +222,10 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* desc, const pdmp_solve_opt
 int32_t pdmp_ensemble_upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc0_per_traj,
                                  const int64_t* xd0, int32_t xd0_per_traj);
 /* Launch the ensemble kernel(s) with inputs resident in HBM.  `stream` is a cudaStream_t
- * passed as void* (NULL: the ensemble's own stream).  Asynchronous. */
+ * passed as void*; NULL means the ensemble's own stream, so pass cudaStreamLegacy
+ * ((void*)1) to order the run on the legacy default stream.  Asynchronous: the run starts
+ * after the work already queued on `stream`, and work queued on it later sees the results
+ * (that is how the caller's NCCL all-reduce of the statistics is ordered). */
 int32_t pdmp_ensemble_run(pdmp_ensemble* e, uint64_t seed, void* stream);
 /* The host-buffer step: upload initial conditions from HOST memory (NULL: keep the resident
  * ones), run, and stream every chunk's results to pinned host staging while later chunks still

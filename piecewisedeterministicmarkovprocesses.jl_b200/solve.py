@@ -90,6 +90,13 @@ class Ensemble:
         _lib.check(L.pdmp_ensemble_upload_ics(self._h, pc, per_c, pd, per_d))
 
     def run(self, seed=0, stream=None):
+        """Asynchronous resident run.  `stream`: None = the ensemble's own stream; otherwise a
+        cudaStream_t handle as an integer (e.g. torch.cuda.current_stream().cuda_stream) — the run is
+        ordered after everything already queued on it, and work queued on it afterwards sees the results.
+        Handle 0 (the legacy default stream, what torch's default stream reports) is passed as
+        cudaStreamLegacy, because NULL means "own stream" in the C ABI."""
+        if stream is not None and int(stream) == 0:
+            stream = 1          # cudaStreamLegacy
         _lib.check(_lib.lib().pdmp_ensemble_run(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, stream))
 
     def run_host(self, seed=0, xc0=None, xd0=None, records=True, copy=False):

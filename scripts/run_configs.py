@@ -69,15 +69,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         best = None
+        stream = torch.cuda.current_stream().cuda_stream
         for r in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
-            ens.run(seed=r)
+            e0.record()
+            ens.run(seed=r, stream=stream)          # joins back onto `stream`: e1 sees the whole step
             if world > 1 and kw.get("sample_times") is not None:
                 P.distributed.allreduce_stats_device(ens, dev)
+            e1.record()
             c = ens.counters()
             torch.cuda.synchronize()
             wall = time.perf_counter() - t0
-            step_ms = c["kernel_ms"] + c["compact_ms"]
+            step_ms = e0.elapsed_time(e1)           # device time of kernel(s) + scan + compaction (+ all-reduce)
             if best is None or step_ms < best[0]:
                 best = (step_ms, c, wall)
         step_ms, c, wall = best
@@ -135,8 +139,7 @@ def main():
         st = list(10.0 * np.arange(1, 17) / 16)
         out, res = throughput("C5", "tcp2d", P.CHVGPU("tcp2d"), n, reps=2, problem=P.models.problem("tcp2d", tspan=(0.0, 10.0)),
                               n_jumps=2000, no_records=True, sample_times=st, hist=[(0, 0.0, 4.0), (1, 0.0, 4.0)], hist_bins=256)
-        if world > 1:
-            res = P.distributed.allreduce_stats_host(res)
+        # (the statistics were all-reduced on the device inside the timed step: `res` is global already)
         out["mean_xc_at_tf"] = res.mean()[-1, :2].tolist()
         out["var_xc_at_tf"] = res.var()[-1, :2].tolist()
         out["count_at_tf"] = float(res.stat_count[-1, 0])

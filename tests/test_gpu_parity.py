@@ -423,3 +423,24 @@ def test_xd_transport_widths(G):
     ev = G.models.problem("neuron_eva")   # a Delta may move xd arbitrarily: auto stays at int32
     c = G.solve(ev, G.RejectionGPU("neuron_eva"), trajectories=64, n_jumps=50, seed=2, xd_transport="auto")
     assert c.xd.dtype == np.int32
+
+
+def test_run_is_ordered_on_the_callers_stream(G):
+    # the statistics all-reduce of the multi-GPU path is queued on the caller's stream right after
+    # run(): it must see the finished statistics without any host synchronisation in between
+    import torch
+    pb = G.models.problem("tcp2d", tspan=(0.0, 10.0))
+    st = list(10.0 * np.arange(1, 9) / 8)
+    ens = G.Ensemble(pb, G.CHVGPU("tcp2d"), trajectories=300_000, n_jumps=2000, no_records=True, sample_times=st)
+    dev = torch.device("cuda", 0)
+    f, _ = G.distributed.stats_tensors(ens, dev)
+    for stream in (torch.cuda.current_stream(), torch.cuda.Stream()):
+        with torch.cuda.stream(stream):
+            ens.run(seed=5, stream=stream.cuda_stream)
+            snap = f.clone()                       # queued on the same stream, no sync
+        torch.cuda.synchronize()
+        res = ens.fetch(records=False)
+        assert res.stat_count[-1, 0] == 300_000
+        want = np.concatenate([res.stat_count.ravel(), res.stat_sum.ravel(), res.stat_sumsq.ravel()])
+        assert np.array_equal(snap.cpu().numpy(), want)
+    ens.close()
