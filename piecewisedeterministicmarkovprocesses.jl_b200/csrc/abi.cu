@@ -266,8 +266,8 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     {   // phase-scheduler thresholds (tunable for experiments)
         const char* ej = std::getenv("PDMP_JUMP_THRESH");
         const char* er = std::getenv("PDMP_REFILL_THRESH");
-        P.jump_thresh = ej ? std::max(1, std::atoi(ej)) : 12;
-        P.refill_thresh = er ? std::max(1, std::atoi(er)) : 2;
+        P.jump_thresh = ej ? std::max(1, std::atoi(ej)) : m.sched_jump;
+        P.refill_thresh = er ? std::max(1, std::atoi(er)) : m.sched_refill;
     }
     P.n_sample = o->n_sample_times; P.n_comp = NC + ND; P.hist_n = o->hist_n; P.hist_bins = o->hist_n ? o->hist_bins : 0;
     e->records = !o->no_records;

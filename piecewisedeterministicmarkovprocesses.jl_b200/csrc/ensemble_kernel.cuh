@@ -106,6 +106,7 @@ struct Traj {
     unsigned long long wslot;  // next record slot in the pool
     bool overflow;
     int next_sample;
+    double tnext;       // sample_times[next_sample], or +huge when none is left
 
     // ------------------------------------------------------------------------------
     PDMP_DEV double draw(const KParams& P, bool& exhausted) {
@@ -203,62 +204,81 @@ struct Traj {
         }
     }
 
-    // ---- plain-F flow of the anchor (xs, ts) to tau: sample times and the "last bit" ----
-    // reference src/chvdiffeq.jl:160-168 (one fresh ODE solve per call there; here an adaptive
-    // loop with the same pair and the user's tolerances, chained from the last anchor)
-    PDMP_DEV bool flow_anchor_to(const KParams& P, double tau, unsigned& aux_attempts, int& fail) {
-        if constexpr (M::ZERO_FLOW) { ts = tau; return true; }
-        if (!(tau > ts)) return true;
-        double hh = tau - ts;
+    // ---- plain-F flow of (x, t) to tau, either direction; adaptive, same pair, user tolerances ----
+    PDMP_DEV bool flow_F(const KParams& P, double (&x)[NC], double& t, double tau, unsigned& aux_attempts, int& fail) {
+        if constexpr (M::ZERO_FLOW) { t = tau; return true; }
+        if (t == tau) return true;
+        const double dir = tau > t ? 1.0 : -1.0;
+        double hh = tau - t;
         PIController c2; c2.init();
         double f1[NC];
-        M::F(f1, xs, xd, P.parms, ts);
-        auto rhs = [&](const double* x, double* dx, double t) { M::F(dx, x, xd, P.parms, t); };
+        M::F(f1, x, xd, P.parms, t);
+        auto rhs = [&](const double* xx, double* dx, double tt) { M::F(dx, xx, xd, P.parms, tt); };
         const unsigned budget = (unsigned)min((long long)0x7fffffff, P.max_attempts);
-        while (ts < tau) {
+        while (t != tau) {
             bool clipped = false;
             double step = hh;
-            if (step >= tau - ts) { step = tau - ts; clipped = true; }
+            if (dir * step >= dir * (tau - t)) { step = tau - t; clipped = true; }
             double xn[NC], f7[NC];
-            const double e2 = rk_attempt<Tab, NC>(rhs, xs, f1, ts, step, xn, f7, P.reltol, P.abstol);
+            const double e2 = rk_attempt<Tab, NC>(rhs, x, f1, t, step, xn, f7, P.reltol, P.abstol);
             if (++aux_attempts > budget) { fail = PDMP_ST_MAX_ATTEMPTS; return false; }
             const bool accept = e2 <= (double)NC;
             double fac;
             if (!(e2 == e2) || isinf(e2)) {
                 bool ok = true;
 #pragma unroll
-                for (int i = 0; i < NC; ++i) ok = ok && isfinite(xs[i]) && isfinite(f1[i]);
-                if (!ok || !(ts + 0.2 * step > ts)) { fail = PDMP_ST_NAN; return false; }
+                for (int i = 0; i < NC; ++i) ok = ok && isfinite(x[i]) && isfinite(f1[i]);
+                if (!ok || !(t + 0.2 * step != t)) { fail = PDMP_ST_NAN; return false; }
                 fac = 0.2;
             } else {
                 fac = c2.step(e2 * (1.0 / NC), accept);
             }
             if (accept) {
 #pragma unroll
-                for (int i = 0; i < NC; ++i) { xs[i] = xn[i]; f1[i] = f7[i]; }
-                double tn = ts + step;
+                for (int i = 0; i < NC; ++i) { x[i] = xn[i]; f1[i] = f7[i]; }
+                double tn = t + step;
                 if (clipped || fabs(tn - tau) < 100.0 * 2.220446049250313e-16 * fmax(fabs(tn), fabs(tau))) tn = tau;
-                ts = tn;
+                t = tn;
             }
             hh = step * fac;
         }
         return true;
     }
-
-    PDMP_DEV bool sample_until(const KParams& P, double* sstat, unsigned* shist, double tlimit, unsigned& aux,
-                               int& fail) {
-        if constexpr (STATS) {
-            while (next_sample < P.n_sample) {
-                const double tau = __ldg(P.sample_times + next_sample);
-                if (!(tau <= tlimit)) break;
-                if (!flow_anchor_to(P, tau, aux, fail)) return false;
-                accumulate(P, sstat, shist, next_sample, xs);
-                ++next_sample;
-            }
-        }
-        return true;
+    // the "last bit": plain-F flow of the anchor (state at the last executed jump) to tf,
+    // reference src/chvdiffeq.jl:160-168 (a fresh ODE solve there)
+    PDMP_DEV bool flow_anchor_to(const KParams& P, double tau, unsigned& aux_attempts, int& fail) {
+        if (!(tau > ts)) return true;
+        return flow_F(P, xs, ts, tau, aux_attempts, fail);
     }
 
+    // ---- ensemble statistics at the fixed sample times -----------------------------------
+    // A lane stops (LANE_WAIT) as soon as an accepted step carries it past the next sample time,
+    // so the sample lies within the step just taken: it is reached by flowing plain F BACKWARDS
+    // from the current state (typically one RK attempt), and the current xd is the state there.
+    // time the trajectory has reached (CHV: the time slot; Rejection: s is time)
+    PDMP_DEV double threshold_time() const { return ALG == PDMP_ALG_CHV ? y[D - 1] : s; }
+    PDMP_DEV bool sample_due(const KParams& P) const {
+        if constexpr (!STATS) return false;
+        return tnext <= threshold_time();   // sample times are <= tf by contract; +huge when none is left
+    }
+    PDMP_DEV int pre_sample(const KParams& P, double* sstat, unsigned* shist, unsigned& aux) {
+        int fail = PDMP_ST_OK;
+        if constexpr (STATS) {
+            const double tcur = threshold_time(), tlim = fmin(tcur, P.tf);
+            int last = next_sample;
+            while (last < P.n_sample && __ldg(P.sample_times + last) <= tlim) ++last;
+            double xb[NC], tb = tcur;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) xb[i] = y[i];
+            for (int j = last - 1; j >= next_sample; --j) {      // latest first: always a short backward leg
+                if (!flow_F(P, xb, tb, __ldg(P.sample_times + j), aux, fail)) return fail;
+                accumulate(P, sstat, shist, j, xb);
+            }
+            next_sample = last;
+            tnext = last < P.n_sample ? __ldg(P.sample_times + last) : 1.7976931348623157e308;
+        }
+        return fail;
+    }
 
     // ---- init!(problem) + integrator construction --------------------------------------
     // reference src/problem.jl:150-161, src/chvdiffeq.jl:97-136, src/rejectiondiffeq.jl:91-116
@@ -286,6 +306,7 @@ struct Traj {
         attempts = 0;
         nrec_stored = 0; seg_left = 0; seg_k = 0; wslot = 0; overflow = false;
         next_sample = 0;
+        tnext = (STATS && P.n_sample > 0) ? __ldg(P.sample_times) : 1.7976931348623157e308;
         pi.init();
         write_record(P, P.t0, xs);  // the initial point is always kept (resize!(..., 1))
 
@@ -341,29 +362,11 @@ struct Traj {
     }
 
     // ---- chvjump, reference src/chvdiffeq.jl:24-74, and the tail of the while body :145-157 ----
-    // time of the threshold the trajectory sits on (CHV: the time slot; Rejection: s is time)
-    PDMP_DEV double threshold_time() const { return ALG == PDMP_ALG_CHV ? y[D - 1] : s; }
-    // a fixed sample time lies at or before this threshold: the anchor flow must run first
-    PDMP_DEV bool sample_due(const KParams& P) const {
-        if constexpr (!STATS) return false;
-        return next_sample < P.n_sample && __ldg(P.sample_times + next_sample) <= fmin(threshold_time(), P.tf);
-    }
-    // the sampling part of the threshold section, separable so that the slot-pool kernel can run
-    // it as its own (rare, divergent) pass and keep the jump pass converged; returns a status
-    PDMP_DEV int pre_sample(const KParams& P, double* sstat, unsigned* shist, unsigned& aux) {
-        int fail = PDMP_ST_OK;
-        sample_until(P, sstat, shist, fmin(threshold_time(), P.tf), aux, fail);
-        return fail;
-    }
-
-    template <bool SAMPLED = false>
-    PDMP_DEV bool chv_threshold(const KParams& P, double* sstat, unsigned* shist, unsigned& aux,
-                                unsigned& jumps) {
+    // (the sample times at or before this threshold were handled by pre_sample)
+    PDMP_DEV bool chv_threshold(const KParams& P, unsigned& aux, unsigned& jumps) {
         int fail = PDMP_ST_OK;
         bool ex = false;
         const double tj = y[NC];
-        if constexpr (!SAMPLED)
-            if (!sample_until(P, sstat, shist, fmin(tj, P.tf), aux, fail)) { finish(P, fail); return true; }
         if (P.save_pre && tj <= P.tf) write_record(P, tj, y);  // :41-48
         double rate[NR];
         M::rates(rate, y, xd, P.parms, tj);  // :51, rates at the PRE-jump state
@@ -398,14 +401,10 @@ struct Traj {
     }
 
     // ---- rejectionjump, reference src/rejectiondiffeq.jl:14-74, and :121-139 ----
-    template <bool SAMPLED = false>
-    PDMP_DEV bool rej_candidate(const KParams& P, double* sstat, unsigned* shist, unsigned& aux,
-                                unsigned& jumps) {
+    PDMP_DEV bool rej_candidate(const KParams& P, unsigned& aux, unsigned& jumps) {
         int fail = PDMP_ST_OK;
         bool ex = false;
         const double tc = s;
-        if constexpr (!SAMPLED)
-            if (!sample_until(P, sstat, shist, fmin(tc, P.tf), aux, fail)) { finish(P, fail); return true; }
         double rate[NR];
         M::rates(rate, y, xd, P.parms, tc);
         double tot = rate[0];
@@ -456,6 +455,12 @@ struct MinBlocks {
 // lane states of the phase scheduler
 enum { LANE_DEAD = 0, LANE_RUN = 1, LANE_WAIT = 2, LANE_EXHAUSTED = 3 };
 
+// default scheduler thresholds; a model may define `static constexpr int SCHED_JUMP, SCHED_REFILL`
+template <class M, class = void> struct SchedDefaults { static constexpr int jump = 12, refill = 2; };
+template <class M> struct SchedDefaults<M, decltype((void)M::SCHED_JUMP, (void)M::SCHED_REFILL)> {
+    static constexpr int jump = M::SCHED_JUMP, refill = M::SCHED_REFILL;
+};
+
 template <class M, class Tab, int ALG, bool RECORDS, bool STATS>
 __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kernel(const __grid_constant__ KParams P) {
     using T = Traj<M, Tab, ALG, RECORDS, STATS>;
@@ -483,6 +488,11 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
     //   JUMP   the threshold section for every WAIT lane — deferred until enough lanes wait, so
     //          that its ~300 instructions are issued for many lanes at once instead of ~5
     //   REFILL trajectories for DEAD lanes from the global cursor (warp-aggregated atomic)
+    // Greedy rule behind the JUMP threshold: with w waiting and r running lanes, landing probability
+    // p per lane and RK iteration, n iterations since the last JUMP and phase costs J (JUMP) and R (one
+    // RK iteration), one more RK iteration pays iff p r (n + J/R) > w.  For TCP (p = 0.18, J/R = 1.5)
+    // that gives w ~ 14-16, for Morris-Lecar (p = 0.5, an RK iteration of 18 exp) w ~ 6: hence the
+    // per-model defaults SchedDefaults<M> (measured sweeps: profiles/r1_sched_sweep.txt).
     for (;;) {
         const unsigned m_run = __ballot_sync(0xffffffffu, st == LANE_RUN);
         const unsigned m_wait = __ballot_sync(0xffffffffu, st == LANE_WAIT);
@@ -526,11 +536,14 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
                 }
             }
             if (st == LANE_WAIT) {
-                ++c_cands;
                 bool done;
                 if (fc) { tr.finish(P, fc); done = true; }
-                else if constexpr (ALG == PDMP_ALG_CHV) done = tr.template chv_threshold<true>(P, sstat, shist, c_aux, c_jumps);
-                else done = tr.template rej_candidate<true>(P, sstat, shist, c_aux, c_jumps);
+                else if (!NO_FLOW && tr.s != tr.tstop) done = false;   // stopped for a sample only: back to stepping
+                else {
+                    ++c_cands;
+                    if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, c_aux, c_jumps);
+                    else done = tr.rej_candidate(P, c_aux, c_jumps);
+                }
                 if (done) st = LANE_DEAD;
                 else if (NO_FLOW) { tr.s = tr.tstop; }   // F = F_dummy: next candidate directly
                 else st = LANE_RUN;
@@ -576,6 +589,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
                         st = LANE_WAIT;
                     }
                     tr.s = sn;
+                    if constexpr (STATS) if (tr.sample_due(P)) st = LANE_WAIT;   // stepped past a sample time
                     if (clipped && P.tstop_policy == 1) hnext = fmax(hnext, hprop);
                 } else {
                     ++c_rejects;
@@ -611,6 +625,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
 struct ModelEntry {
     pdmp_model_info info;
     int rec_words;  // RecLayout::WORDS
+    int sched_jump, sched_refill;  // SchedDefaults<M>
     // launch(alg, ode, records, stats, P, grid, smem, stream): returns cudaError_t
     cudaError_t (*launch)(int alg, int ode, bool records, bool stats, const KParams& P, int grid, size_t smem,
                           cudaStream_t stream);
@@ -734,6 +749,7 @@ ModelEntry make_entry(int id) {
     e.info.has_bound = M::HAS_BOUND; e.info.has_delta = M::HAS_DELTA; e.info.zero_flow = M::ZERO_FLOW;
     for (int i = 0; M::NAME[i] && i < 31; ++i) e.info.name[i] = M::NAME[i];
     e.rec_words = RecLayout<M>::WORDS;
+    e.sched_jump = SchedDefaults<M>::jump; e.sched_refill = SchedDefaults<M>::refill;
     e.launch = &model_launch<M>;
     e.occupancy = &model_occupancy<M>;
     e.compact = &model_compact<M>;

@@ -27,6 +27,7 @@ struct TcpDev {  // examples/tcp.jl:25-45
     static constexpr int NC = 1, ND = 2, NR = 2, NP = 1;
     static constexpr bool HAS_BOUND = true, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = true;
     static constexpr const char* NAME = "tcp";
+    static constexpr int SCHED_JUMP = 16, SCHED_REFILL = 2;   // ~5.5 cheap RK attempts per jump
     PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) {
         dx[0] = (xd[0] & 1) ? -1.0 : 1.0;  // mod(xd[1], 2) == 0 ? 1 : -1
     }
@@ -49,6 +50,7 @@ struct Tcp2dDev {  // examples/tcp2d.jl:4-25
     static constexpr int NC = 2, ND = 2, NR = 2, NP = 1;
     static constexpr bool HAS_BOUND = false, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;
     static constexpr const char* NAME = "tcp2d";
+    static constexpr int SCHED_JUMP = 16, SCHED_REFILL = 8;   // short trajectories: batch the initialisations
     PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) {
         if ((xd[0] & 1) == 0) { dx[0] = 1.0; dx[1] = -1.0 * x[1]; }
         else { dx[0] = -1.0 * x[0]; dx[1] = 1.0; }
@@ -68,6 +70,7 @@ struct MorrisLecarDev {  // examples/morris_lecar.jl:8-28
     static constexpr int NC = 1, ND = 4, NR = 4, NP = 15;
     static constexpr bool HAS_BOUND = false, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;
     static constexpr const char* NAME = "morris_lecar";
+    static constexpr int SCHED_JUMP = 6, SCHED_REFILL = 2;    // ~2 expensive RK attempts (18 exp) per jump
     enum { v_Na, g_Na, v_K, g_K, v_L, g_L, I_app, gamma_na, k_na, beta_na, gamma_k, k_k, beta_k, M, N };
     PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) {
         dx[0] = (double)xd[1] / p[N] * (p[g_Na] * (p[v_Na] - x[0])) +
