@@ -43,6 +43,10 @@ enum { PDMP_ODE_DP5 = 0, PDMP_ODE_TSIT5 = 1 };
 
 enum { PDMP_RNG_PHILOX = 0, PDMP_RNG_REPLAY = 1 };
 
+/* FP32: state and Runge-Kutta stage arithmetic in float; the integration variable, thresholds,
+ * step size and jump times stay double (CHV: the time slot is refreshed from a double shadow
+ * after every accepted step).  Meant for reltol >= 1e-6; models whose state leaves the float
+ * range (TCP on long horizons) flag the affected trajectories NO_PROGRESS / NAN. */
 enum { PDMP_PREC_FP64 = 0, PDMP_PREC_FP32 = 1 };
 
 /* per-trajectory status (result.status[i]) */

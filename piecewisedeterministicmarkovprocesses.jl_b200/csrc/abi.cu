@@ -204,7 +204,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     const int NC = m.info.n_c, ND = m.info.n_d, NR = m.info.n_r;
     if (o->n_jumps < 1) return fail(PDMP_ERR_INVALID, "n_jumps must be >= 1 and finite");
     if (!(d->t0 < d->tf)) return fail(PDMP_ERR_INVALID, "tspan must satisfy t0 < tf");
-    if (!(o->reltol > 0) || !(o->abstol > 0)) return fail(PDMP_ERR_INVALID, "reltol and abstol must be > 0");
+    if (!(o->reltol > 0) || !(o->abstol >= 1e-300)) return fail(PDMP_ERR_INVALID, "reltol must be > 0 and abstol >= 1e-300");
     if (d->n_parms < m.info.n_parms || d->n_parms > MAXP)
         return fail(PDMP_ERR_MODEL, std::string("model '") + m.info.name + "' reads " +
                                         std::to_string(m.info.n_parms) + " parameters");
@@ -213,7 +213,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     if (o->algorithm == PDMP_ALG_REJECTION && !m.info.has_bound)
         return fail(PDMP_ERR_MODEL, std::string("model '") + m.info.name + "' has no rate bound: Rejection unavailable");
     if (o->ode != PDMP_ODE_DP5 && o->ode != PDMP_ODE_TSIT5) return fail(PDMP_ERR_INVALID, "ode");
-    if (o->precision != PDMP_PREC_FP64) return fail(PDMP_ERR_UNSUPPORTED, "only FP64 is built in this version");
+    if (o->precision != PDMP_PREC_FP64 && o->precision != PDMP_PREC_FP32) return fail(PDMP_ERR_INVALID, "precision");
     if (o->rng_mode == PDMP_RNG_REPLAY && (!o->replay_u || !o->replay_stride)) return fail(PDMP_ERR_INVALID, "replay_u");
     if (o->xd_bytes != 0 && o->xd_bytes != 8 && o->xd_bytes != 4 && o->xd_bytes != 2) return fail(PDMP_ERR_INVALID, "xd_bytes must be 0, 8, 4 or 2");
     if (o->hist_n < 0 || o->hist_n > MAXH) return fail(PDMP_ERR_INVALID, "hist_n must be <= 4");
@@ -390,7 +390,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     // persistent launch shape: resident CTAs per SM x SM count, capped by the work of a chunk
     int bps = 0, sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
-    CK(m.occupancy(o->algorithm, o->ode, e->records, e->stats, e->smem, &bps));
+    CK(m.occupancy(o->algorithm, o->ode, o->precision, e->records, e->stats, e->smem, &bps));
     if (bps < 1) return fail(PDMP_ERR_CUDA, "kernel does not fit on an SM");
     e->grid = std::max(1, bps * sms);
     CK(cudaStreamSynchronize(s0));  // inputs are borrowed only for the duration of the call
@@ -504,7 +504,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
         Pk.nrec += a; Pk.njumps += a; Pk.nrejected += a; Pk.status += a;
         if (k >= NS) CK(cudaMemsetAsync(e->d_ctl + 2 * q, 0, 2 * sizeof(unsigned long long), st));
         const int grid = (int)std::min<unsigned long long>(e->grid, (Pk.n_traj + BLOCK - 1) / BLOCK);
-        CK(e->m->launch(e->o.algorithm, e->o.ode, e->records, e->stats, Pk, std::max(grid, 1), e->smem, st));
+        CK(e->m->launch(e->o.algorithm, e->o.ode, e->o.precision, e->records, e->stats, Pk, std::max(grid, 1), e->smem, st));
         CK(cudaEventRecord(e->ev_kend[q], st));
         if (e->records && k > 0) CK(cudaStreamWaitEvent(st, e->ev_base[k - 1], 0));  // offsets[a] (start of this chunk) is final
         CK(cudaEventRecord(e->ev_c0[k], st));

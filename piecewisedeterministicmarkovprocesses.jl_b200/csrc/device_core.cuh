@@ -36,19 +36,26 @@ PDMP_DEV double rcp_fast(double x) {
 #endif
 }
 
-// same, for arguments known to be positive and in the normal range (error weights
-// abstol + |u| reltol): no fallback branch
-PDMP_DEV double rcp_pos(double x) {
+// error weights abstol + |u| reltol (positive, normal range) only feed the step controller, whose
+// powers are FP32 anyway: the bare MUFU.RCP64H seed (>= 20 mantissa bits, PTX rcp.approx.ftz.f64)
+// is enough — a relative error of 1e-6 in EEst moves an accept/reject decision only when EEst
+// is within 1e-6 of 1
+PDMP_DEV double rcp_weight(double x) {
 #ifdef PDMP_EXACT_DIV
     return 1.0 / x;
 #else
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+    return r;
 #endif
+}
+
+// FP32 flavours (the optional PDMP_PREC_FP32 kernels)
+PDMP_DEV float rcp_fast(float x) { return __frcp_rn(x); }
+PDMP_DEV float rcp_weight(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -121,11 +128,40 @@ static __constant__ double c_ts5_bt[7] = {-0.00178001105222577714, -0.0008164344
                                           1.0 / 66.0};
 static __constant__ double c_ts5_c[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
 
+// FP32 copies of the tableaus (rounded once, at compile time)
+static __constant__ float c_dp5_af[6][6] = {
+    {(float)(1.0 / 5), (float)(0), (float)(0), (float)(0), (float)(0), (float)(0)},
+    {(float)(3.0 / 40), (float)(9.0 / 40), (float)(0), (float)(0), (float)(0), (float)(0)},
+    {(float)(44.0 / 45), (float)(-56.0 / 15), (float)(32.0 / 9), (float)(0), (float)(0), (float)(0)},
+    {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), (float)(0), (float)(0)},
+    {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176), (float)(-5103.0 / 18656), (float)(0)},
+    {(float)(35.0 / 384), (float)(0.0), (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784), (float)(11.0 / 84)}};
+static __constant__ float c_dp5_btf[7] = {(float)(71.0 / 57600), (float)(0.0), (float)(-71.0 / 16695), (float)(71.0 / 1920), (float)(-17253.0 / 339200),
+                                          (float)(22.0 / 525), (float)(-1.0 / 40)};
+static __constant__ float c_dp5_cf[7] = {(float)(0.0), (float)(1.0 / 5), (float)(3.0 / 10), (float)(4.0 / 5), (float)(8.0 / 9), (float)(1.0), (float)(1.0)};
+static __constant__ float c_ts5_af[6][6] = {
+    {(float)(0.161), (float)(0), (float)(0), (float)(0), (float)(0), (float)(0)},
+    {(float)(-0.008480655492356989), (float)(0.335480655492357), (float)(0), (float)(0), (float)(0), (float)(0)},
+    {(float)(2.8971530571054935), (float)(-6.359448489975075), (float)(4.3622954328695815), (float)(0), (float)(0), (float)(0)},
+    {(float)(5.325864828439257), (float)(-11.748883564062828), (float)(7.4955393428898365), (float)(-0.09249506636175525), (float)(0), (float)(0)},
+    {(float)(5.86145544294642), (float)(-12.92096931784711), (float)(8.159367898576159), (float)(-0.071584973281401), (float)(-0.028269050394068383), (float)(0)},
+    {(float)(0.09646076681806523), (float)(0.01), (float)(0.4798896504144996), (float)(1.379008574103742), (float)(-3.290069515436081), (float)(2.324710524099774)}};
+static __constant__ float c_ts5_btf[7] = {(float)(-0.00178001105222577714), (float)(-0.0008164344596567469), (float)(0.007880878010261995),
+                                          (float)(-0.1447110071732629),     (float)(0.5823571654525552),     (float)(-0.45808210592918697),
+                                          (float)(1.0 / 66.0)};
+static __constant__ float c_ts5_cf[7] = {(float)(0.0), (float)(0.161), (float)(0.327), (float)(0.9), (float)(0.9800255409045097), (float)(1.0), (float)(1.0)};
+
 struct TabDP5 {
     static constexpr int ID = 0;
-    PDMP_DEV static double A(int s, int j) { return c_dp5_a[s][j]; }
-    PDMP_DEV static double BT(int j) { return c_dp5_bt[j]; }
-    PDMP_DEV static double C(int i) { return c_dp5_c[i]; }
+    template <class R> PDMP_DEV static R A(int s, int j) {
+        if constexpr (sizeof(R) == 4) return c_dp5_af[s][j]; else return c_dp5_a[s][j];
+    }
+    template <class R> PDMP_DEV static R BT(int j) {
+        if constexpr (sizeof(R) == 4) return c_dp5_btf[j]; else return c_dp5_bt[j];
+    }
+    template <class R> PDMP_DEV static R C(int i) {
+        if constexpr (sizeof(R) == 4) return c_dp5_cf[i]; else return c_dp5_c[i];
+    }
     __host__ __device__ static constexpr double c(int i) {
         constexpr double C[7] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
         return C[i];
@@ -149,9 +185,15 @@ struct TabDP5 {
 
 struct TabTsit5 {
     static constexpr int ID = 1;
-    PDMP_DEV static double A(int s, int j) { return c_ts5_a[s][j]; }
-    PDMP_DEV static double BT(int j) { return c_ts5_bt[j]; }
-    PDMP_DEV static double C(int i) { return c_ts5_c[i]; }
+    template <class R> PDMP_DEV static R A(int s, int j) {
+        if constexpr (sizeof(R) == 4) return c_ts5_af[s][j]; else return c_ts5_a[s][j];
+    }
+    template <class R> PDMP_DEV static R BT(int j) {
+        if constexpr (sizeof(R) == 4) return c_ts5_btf[j]; else return c_ts5_bt[j];
+    }
+    template <class R> PDMP_DEV static R C(int i) {
+        if constexpr (sizeof(R) == 4) return c_ts5_cf[i]; else return c_ts5_c[i];
+    }
     __host__ __device__ static constexpr double c(int i) {
         constexpr double C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
         return C[i];
@@ -180,38 +222,39 @@ struct TabTsit5 {
 // e2 = sum_i (err_i / (abstol + max(|u_i|,|unew_i|) reltol))^2  (EEst^2 * D).
 // All arrays are compile-time indexed: they live in registers.
 // ---------------------------------------------------------------------------------------
-template <class Tab, int D, class RHS>
-PDMP_DEV double rk_attempt(RHS&& f, const double (&u)[D], const double (&k1)[D], double t, double h,
-                           double (&unew)[D], double (&k7)[D], double reltol, double abstol) {
-    double k[7][D];
+template <class Tab, int D, class R, class RHS>
+PDMP_DEV R rk_attempt(RHS&& f, const R (&u)[D], const R (&k1)[D], R t, R h, R (&unew)[D], R (&k7)[D], R reltol,
+                      R abstol, R& inc_last) {
+    R k[7][D];
 #pragma unroll
     for (int i = 0; i < D; ++i) k[0][i] = k1[i];
 #pragma unroll
     for (int s = 1; s < 7; ++s) {
-        double us[D];
+        R us[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-            double acc = Tab::A(s - 1, 0) * k[0][i];
+            R acc = Tab::template A<R>(s - 1, 0) * k[0][i];
 #pragma unroll
             for (int j = 1; j < s; ++j)
-                if (Tab::a(s - 1, j) != 0.0) acc = fma(Tab::A(s - 1, j), k[j][i], acc);
+                if (Tab::a(s - 1, j) != 0.0) acc = fma(Tab::template A<R>(s - 1, j), k[j][i], acc);
             us[i] = fma(h, acc, u[i]);
+            if (s == 6 && i == D - 1) inc_last = h * acc;   // increment of the last component (FP32 time shadow)
         }
         if (s == 6) {
 #pragma unroll
             for (int i = 0; i < D; ++i) unew[i] = us[i];
         }
-        f(us, k[s], fma(Tab::C(s), h, t));
+        f(us, k[s], fma(Tab::template C<R>(s), h, t));
     }
-    double e2 = 0.0;
+    R e2 = R(0);
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-        double acc = Tab::BT(0) * k[0][i];
+        R acc = Tab::template BT<R>(0) * k[0][i];
 #pragma unroll
         for (int j = 1; j < 7; ++j)
-            if (Tab::bt(j) != 0.0) acc = fma(Tab::BT(j), k[j][i], acc);
-        const double sc = fma(fmax(fabs(u[i]), fabs(unew[i])), reltol, abstol);
-        const double r = (h * acc) * rcp_pos(sc);
+            if (Tab::bt(j) != 0.0) acc = fma(Tab::template BT<R>(j), k[j][i], acc);
+        const R sc = fma(fmax(fabs(u[i]), fabs(unew[i])), reltol, abstol);
+        const R r = (h * acc) * rcp_weight(sc);
         e2 = fma(r, r, e2);
         k7[i] = k[6][i];
     }
@@ -237,8 +280,8 @@ struct PIController {
     // returns the factor f such that h_next = h * f
     //   accept : f = 1/q,  q = clamp(EEst^b1 / qold^b2 / gamma, 1/qmax, 1/qmin)
     //   reject : f = 1/min(1/qmin, EEst^b1 / gamma)
-    PDMP_DEV double step(double EEst2, bool accept) {
-        const float l = lg2_approx((float)EEst2);            // log2(EEst^2); -inf for EEst = 0
+    PDMP_DEV float step(float EEst2, bool accept) {
+        const float l = lg2_approx(EEst2);            // log2(EEst^2); -inf for EEst = 0
         const float lq11 = 0.07f * l;                        // log2(EEst^beta1), beta1 = 7/50
         const float lg = 0.15200309344f;                     // -log2(gamma), gamma = 9/10
         float lq;
@@ -249,7 +292,7 @@ struct PIController {
         } else {
             lq = fminf(lq11 + lg, 2.32192809489f);
         }
-        return (double)ex2_approx(-lq);
+        return ex2_approx(-lq);
     }
 };
 

@@ -80,21 +80,27 @@ struct RecLayout {
 // geometric segment sizes: segment k holds REC_BLOCK << (k >> 2) records (4 segments per doubling)
 __host__ __device__ inline unsigned seg_records(int k) { return (unsigned)REC_BLOCK << (k >> 2); }
 
-template <class M, class Tab, int ALG, bool RECORDS, bool STATS>
+// R is the real type of the state and of the stage arithmetic: double, or float for the optional
+// PDMP_PREC_FP32 kernels.  Time-like scalars (s, thresholds, step size, jump times) stay double
+// in both; in FP32 CHV kernels the time slot y[NC] is refreshed after every accepted step from a
+// double shadow `tacc` that accumulates the step increments, so that time does not drift.
+template <class M, class Tab, int ALG, bool RECORDS, bool STATS, class R>
 struct Traj {
     static constexpr int NC = M::NC, ND = M::ND, NR = M::NR;
     static constexpr int D = (ALG == PDMP_ALG_CHV) ? NC + 1 : NC;
+    static constexpr bool SHADOW_T = (ALG == PDMP_ALG_CHV) && sizeof(R) == 4;
     using RL = RecLayout<M>;
 
     // ---- integrator state ----
-    double y[D];        // CHV: (xc, t) in the time-change variable s ; Rejection: xc in time t
-    double k1[D];       // FSAL
+    R y[D];             // CHV: (xc, t) in the time-change variable s ; Rejection: xc in time t
+    R k1[D];            // FSAL
+    double tacc;        // SHADOW_T only: the time slot in double
     double s, tstop, h; // integration variable, next threshold, proposed step
     PIController pi;
     // ---- PDMP state ----
     int xd[ND];
     double tlast;       // reference `t` of the outer loop (time of the last threshold)
-    double xs[NC], ts;  // anchor of the plain-F flow: state/time at the last executed jump
+    R xs[NC]; double ts;  // anchor of the plain-F flow: state/time at the last executed jump
                         // (CHV: caract.xc ; Rejection: state at the last candidate)
     long long simnj, nfict;
     unsigned attempts;
@@ -115,13 +121,13 @@ struct Traj {
     }
 
     // (chv::CHV)(xdot, x, caract, t): (F, 1) / Rtot      reference src/chvdiffeq.jl:6-16
-    PDMP_DEV void field(const KParams& P, const double* x, double* dx, double t) const {
+    PDMP_DEV void field(const KParams& P, const R* x, R* dx, R t) const {
         if constexpr (ALG == PDMP_ALG_CHV) {
             if constexpr (M::HAS_CHV_FIELD) {
                 M::chv_field(dx, x, xd, P.parms);
             } else {
-                const double tau = x[NC];
-                const double inv = rcp_fast(M::rtot(x, xd, P.parms, tau));
+                const R tau = x[NC];
+                const R inv = rcp_fast(M::rtot(x, xd, P.parms, tau));
                 M::F(dx, x, xd, P.parms, tau);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) dx[i] *= inv;
@@ -133,7 +139,7 @@ struct Traj {
     }
 
     // ---- record pool writer ----------------------------------------------------------
-    PDMP_DEV void write_record(const KParams& P, double t, const double* xc) {
+    PDMP_DEV void write_record(const KParams& P, double t, const R* xc) {
         if constexpr (!RECORDS) return;
         if (seg_left == 0) {
             const unsigned nrecs = seg_records(seg_k);
@@ -152,7 +158,7 @@ struct Traj {
         double w[RL::WORDS];
         w[0] = t;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) w[1 + i] = xc[i];
+        for (int i = 0; i < NC; ++i) w[1 + i] = (double)xc[i];
 #pragma unroll
         for (int i = 0; i < RL::XD_WORDS; ++i) {
             const int lo = xd[2 * i];
@@ -169,13 +175,13 @@ struct Traj {
     }
 
     // ---- statistics at a sample time -------------------------------------------------
-    PDMP_DEV void accumulate(const KParams& P, double* sstat, unsigned* shist, int j, const double* xc) {
+    PDMP_DEV void accumulate(const KParams& P, double* sstat, unsigned* shist, int j, const R* xc) {
         if constexpr (!STATS) return;
         const int C = P.n_comp, TC = P.n_sample * C;
         if (P.stats_in_smem) {
 #pragma unroll
             for (int c = 0; c < NC + ND; ++c) {
-                const double v = c < NC ? xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
+                const double v = c < NC ? (double)xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
                 atomicAdd(sstat + j * C + c, 1.0);
                 atomicAdd(sstat + TC + j * C + c, v);
                 atomicAdd(sstat + 2 * TC + j * C + c, v * v);
@@ -183,7 +189,7 @@ struct Traj {
         } else {
 #pragma unroll
             for (int c = 0; c < NC + ND; ++c) {
-                const double v = c < NC ? xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
+                const double v = c < NC ? (double)xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
                 atomicAdd(P.stats + j * C + c, 1.0);
                 atomicAdd(P.stats + TC + j * C + c, v);
                 atomicAdd(P.stats + 2 * TC + j * C + c, v * v);
@@ -194,7 +200,7 @@ struct Traj {
             double v = 0.0;
 #pragma unroll
             for (int q = 0; q < NC + ND; ++q)
-                if (q == c) v = q < NC ? xc[q < NC ? q : 0] : (double)xd[q >= NC ? q - NC : 0];
+                if (q == c) v = q < NC ? (double)xc[q < NC ? q : 0] : (double)xd[q >= NC ? q - NC : 0];
             const double fb = floor((v - P.hist_lo[hh]) * P.hist_scale[hh]);
             int b = fb < 0.0 ? 0 : (fb >= (double)P.hist_bins ? P.hist_bins - 1 : (int)fb);
             if (!(fb == fb)) b = 0;
@@ -205,24 +211,24 @@ struct Traj {
     }
 
     // ---- plain-F flow of (x, t) to tau, either direction; adaptive, same pair, user tolerances ----
-    PDMP_DEV bool flow_F(const KParams& P, double (&x)[NC], double& t, double tau, unsigned& aux_attempts, int& fail) {
+    PDMP_DEV bool flow_F(const KParams& P, R (&x)[NC], double& t, double tau, unsigned& aux_attempts, int& fail) {
         if constexpr (M::ZERO_FLOW) { t = tau; return true; }
         if (t == tau) return true;
         const double dir = tau > t ? 1.0 : -1.0;
         double hh = tau - t;
         PIController c2; c2.init();
-        double f1[NC];
-        M::F(f1, x, xd, P.parms, t);
-        auto rhs = [&](const double* xx, double* dx, double tt) { M::F(dx, xx, xd, P.parms, tt); };
+        R f1[NC];
+        M::F(f1, x, xd, P.parms, (R)t);
+        auto rhs = [&](const R* xx, R* dx, R tt) { M::F(dx, xx, xd, P.parms, tt); };
         const unsigned budget = (unsigned)min((long long)0x7fffffff, P.max_attempts);
         while (t != tau) {
             bool clipped = false;
             double step = hh;
             if (dir * step >= dir * (tau - t)) { step = tau - t; clipped = true; }
-            double xn[NC], f7[NC];
-            const double e2 = rk_attempt<Tab, NC>(rhs, x, f1, t, step, xn, f7, P.reltol, P.abstol);
+            R xn[NC], f7[NC], inc;
+            const R e2 = rk_attempt<Tab, NC, R>(rhs, x, f1, (R)t, (R)step, xn, f7, (R)P.reltol, (R)P.abstol, inc);
             if (++aux_attempts > budget) { fail = PDMP_ST_MAX_ATTEMPTS; return false; }
-            const bool accept = e2 <= (double)NC;
+            const bool accept = e2 <= (R)NC;
             double fac;
             if (!(e2 == e2) || isinf(e2)) {
                 bool ok = true;
@@ -231,7 +237,7 @@ struct Traj {
                 if (!ok || !(t + 0.2 * step != t)) { fail = PDMP_ST_NAN; return false; }
                 fac = 0.2;
             } else {
-                fac = c2.step(e2 * (1.0 / NC), accept);
+                fac = c2.step((float)(e2 * (R)(1.0 / NC)), accept);
             }
             if (accept) {
 #pragma unroll
@@ -256,7 +262,11 @@ struct Traj {
     // so the sample lies within the step just taken: it is reached by flowing plain F BACKWARDS
     // from the current state (typically one RK attempt), and the current xd is the state there.
     // time the trajectory has reached (CHV: the time slot; Rejection: s is time)
-    PDMP_DEV double threshold_time() const { return ALG == PDMP_ALG_CHV ? y[D - 1] : s; }
+    PDMP_DEV double threshold_time() const {
+        if constexpr (SHADOW_T) return tacc;
+        else if constexpr (ALG == PDMP_ALG_CHV) return (double)y[D - 1];
+        else return s;
+    }
     PDMP_DEV bool sample_due(const KParams& P) const {
         if constexpr (!STATS) return false;
         return tnext <= threshold_time();   // sample times are <= tf by contract; +huge when none is left
@@ -267,7 +277,8 @@ struct Traj {
             const double tcur = threshold_time(), tlim = fmin(tcur, P.tf);
             int last = next_sample;
             while (last < P.n_sample && __ldg(P.sample_times + last) <= tlim) ++last;
-            double xb[NC], tb = tcur;
+            R xb[NC];
+            double tb = tcur;
 #pragma unroll
             for (int i = 0; i < NC; ++i) xb[i] = y[i];
             for (int j = last - 1; j >= next_sample; --j) {      // latest first: always a short backward leg
@@ -287,20 +298,21 @@ struct Traj {
         rng.init();
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            y[i] = P.xc0[(P.xc0_per_traj ? (size_t)idx * NC : 0) + i];
+            y[i] = (R)P.xc0[(P.xc0_per_traj ? (size_t)idx * NC : 0) + i];
             xs[i] = y[i];
         }
 #pragma unroll
         for (int i = 0; i < ND; ++i) xd[i] = (int)P.xd0[(P.xd0_per_traj ? (size_t)idx * ND : 0) + i];
         const double E0 = -log(draw(P, exhausted));  // tstop_extended = -log(rand())
         if constexpr (ALG == PDMP_ALG_CHV) {
-            y[NC] = P.t0;  // X_extended[end] = ti
+            y[NC] = (R)P.t0;  // X_extended[end] = ti
             s = 0.0;
             tstop = E0;
         } else {
             s = P.t0;
-            tstop = E0 / M::bound(y, xd, P.parms, P.t0) + P.t0;  // src/rejectiondiffeq.jl:105-107
+            tstop = E0 / (double)M::bound(y, xd, P.parms, (R)P.t0) + P.t0;  // src/rejectiondiffeq.jl:105-107
         }
+        tacc = P.t0;
         tlast = P.t0; ts = P.t0;
         simnj = 1; nfict = 0;
         attempts = 0;
@@ -311,25 +323,25 @@ struct Traj {
         write_record(P, P.t0, xs);  // the initial point is always kept (resize!(..., 1))
 
         // Hairer-Norsett-Wanner initial step (OrdinaryDiffEq ode_determine_initdt), order 5
-        field(P, y, k1, s);
+        field(P, y, k1, (R)s);
         double d0 = 0.0, d1 = 0.0;
         double sk[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-            sk[i] = P.abstol + fabs(y[i]) * P.reltol;
-            const double a = y[i] / sk[i], b = k1[i] / sk[i];
+            sk[i] = P.abstol + fabs((double)y[i]) * P.reltol;
+            const double a = (double)y[i] / sk[i], b = (double)k1[i] / sk[i];
             d0 = fma(a, a, d0); d1 = fma(b, b, d1);
         }
         d0 = sqrt(d0 * (1.0 / D)); d1 = sqrt(d1 * (1.0 / D));
         double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
         dt0 = fmin(dt0, 1e9);
-        double u1[D], f1[D];
+        R u1[D], f1[D];
 #pragma unroll
-        for (int i = 0; i < D; ++i) u1[i] = fma(dt0, k1[i], y[i]);
-        field(P, u1, f1, s + dt0);
+        for (int i = 0; i < D; ++i) u1[i] = fma((R)dt0, k1[i], y[i]);
+        field(P, u1, f1, (R)(s + dt0));
         double d2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < D; ++i) { const double a = (f1[i] - k1[i]) / sk[i]; d2 = fma(a, a, d2); }
+        for (int i = 0; i < D; ++i) { const double a = ((double)f1[i] - (double)k1[i]) / sk[i]; d2 = fma(a, a, d2); }
         d2 = sqrt(d2 * (1.0 / D)) / dt0;
         const double dm = fmax(d1, d2);
         // 10^(-(2 + log10 dm)/5) = (100 dm)^(-1/5), evaluated in FP32 (it only seeds the controller)
@@ -366,19 +378,19 @@ struct Traj {
     PDMP_DEV bool chv_threshold(const KParams& P, unsigned& aux, unsigned& jumps) {
         int fail = PDMP_ST_OK;
         bool ex = false;
-        const double tj = y[NC];
+        const double tj = threshold_time();
         if (P.save_pre && tj <= P.tf) write_record(P, tj, y);  // :41-48
-        double rate[NR];
-        M::rates(rate, y, xd, P.parms, tj);  // :51, rates at the PRE-jump state
-        double tot = rate[0];
+        R rate[NR];
+        M::rates(rate, y, xd, P.parms, (R)tj);  // :51, rates at the PRE-jump state
+        R tot = rate[0];
 #pragma unroll
         for (int i = 1; i < NR; ++i) tot += rate[i];  // sum(rate), left to right
-        if (!(tot > 0.0) || isinf(tot)) { finish(P, PDMP_ST_NONPOSITIVE_RATE); return true; }
+        if (!(tot > R(0)) || isinf(tot)) { finish(P, PDMP_ST_NONPOSITIVE_RATE); return true; }
         if (tj < P.tf) {  // :52
             // pfsample, reference src/utils.jl:46-57 (strict <, last index absorbs round-off)
-            const double thr = draw(P, ex) * tot;
+            const R thr = (R)draw(P, ex) * tot;
             int ev = 1;
-            double cw = rate[0];
+            R cw = rate[0];
 #pragma unroll
             for (int i = 1; i < NR; ++i)
                 if (ev == i && cw < thr) { ev = i + 1; cw += rate[i]; }
@@ -386,7 +398,7 @@ struct Traj {
 #pragma unroll
             for (int i = 0; i < ND; ++i) xd[i] += P.nu[(ev - 1) * ND + i];
             if constexpr (M::HAS_DELTA) M::delta(y, xd, P.parms, tj, ev);
-            field(P, y, k1, s);  // u_modified!(integrator, true): FSAL re-evaluated
+            field(P, y, k1, (R)s);  // u_modified!(integrator, true): FSAL re-evaluated
 #pragma unroll
             for (int i = 0; i < NC; ++i) xs[i] = y[i];  // caract.xc .= u
             ts = tj;
@@ -405,27 +417,27 @@ struct Traj {
         int fail = PDMP_ST_OK;
         bool ex = false;
         const double tc = s;
-        double rate[NR];
-        M::rates(rate, y, xd, P.parms, tc);
-        double tot = rate[0];
+        R rate[NR];
+        M::rates(rate, y, xd, P.parms, (R)tc);
+        R tot = rate[0];
 #pragma unroll
         for (int i = 1; i < NR; ++i) tot += rate[i];
-        const double bnd = M::bound(y, xd, P.parms, tc);
+        const R bnd = M::bound(y, xd, P.parms, (R)tc);
         if (!(tot < bnd)) { finish(P, PDMP_ST_BOUND_VIOLATED); return true; }  // @assert :33
-        const bool reject = draw(P, ex) < 1.0 - tot / bnd;   // :35
-        const double dtn = -log(draw(P, ex)) / bnd;          // :36
+        const bool reject = draw(P, ex) < 1.0 - (double)tot / (double)bnd;   // :35
+        const double dtn = -log(draw(P, ex)) / (double)bnd;  // :36
         const bool fire = tc < P.tf && !reject;
         if (fire) {                                          // :41
-            const double thr = draw(P, ex) * tot;            // :55
+            const R thr = (R)draw(P, ex) * tot;              // :55
             int ev = 1;
-            double cw = rate[0];
+            R cw = rate[0];
 #pragma unroll
             for (int i = 1; i < NR; ++i)
                 if (ev == i && cw < thr) { ev = i + 1; cw += rate[i]; }
 #pragma unroll
             for (int i = 0; i < ND; ++i) xd[i] += P.nu[(ev - 1) * ND + i];
             if constexpr (M::HAS_DELTA) M::delta(y, xd, P.parms, tc, ev);
-            field(P, y, k1, s);
+            field(P, y, k1, (R)s);
             ++simnj;                                         // :64
             ++jumps;
         } else {
@@ -446,10 +458,11 @@ struct Traj {
 
 // resident CTAs per SM the kernel is compiled for: small models fit 6 x 128 threads in the
 // register file (<= 80 registers), the larger ones 4 (<= 128 registers)
-template <class M, int ALG>
+template <class M, int ALG, class R>
 struct MinBlocks {
     static constexpr int D = (ALG == PDMP_ALG_CHV) ? M::NC + 1 : M::NC;
-    static constexpr int value = (D <= 2 && M::NR <= 2 && M::ND <= 2) ? 6 : 4;
+    static constexpr bool small = (D <= 2 && M::NR <= 2 && M::ND <= 2);
+    static constexpr int value = sizeof(R) == 4 ? (small ? 7 : 5) : (small ? 6 : 4);
 };
 
 // lane states of the phase scheduler
@@ -461,9 +474,9 @@ template <class M> struct SchedDefaults<M, decltype((void)M::SCHED_JUMP, (void)M
     static constexpr int jump = M::SCHED_JUMP, refill = M::SCHED_REFILL;
 };
 
-template <class M, class Tab, int ALG, bool RECORDS, bool STATS>
-__global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kernel(const __grid_constant__ KParams P) {
-    using T = Traj<M, Tab, ALG, RECORDS, STATS>;
+template <class M, class Tab, int ALG, bool RECORDS, bool STATS, class R>
+__global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_kernel(const __grid_constant__ KParams P) {
+    using T = Traj<M, Tab, ALG, RECORDS, STATS, R>;
     constexpr int D = T::D;
     constexpr bool NO_FLOW = (ALG == PDMP_ALG_REJECTION && M::ZERO_FLOW);
     extern __shared__ double smem[];
@@ -558,14 +571,14 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
             bool clipped = false;
             const double rem = tr.tstop - tr.s;
             if (step >= rem) { step = rem; clipped = true; }
-            double yn[D], k7[D];
-            auto rhs = [&](const double* x, double* dx, double t) { tr.field(P, x, dx, t); };
-            const double e2 = rk_attempt<Tab, D>(rhs, tr.y, tr.k1, tr.s, step, yn, k7, P.reltol, P.abstol);
+            R yn[D], k7[D], inc;
+            auto rhs = [&](const R* x, R* dx, R t) { tr.field(P, x, dx, t); };
+            const R e2 = rk_attempt<Tab, D, R>(rhs, tr.y, tr.k1, (R)tr.s, (R)step, yn, k7, (R)P.reltol, (R)P.abstol, inc);
             ++c_attempts;
-            const bool accept = e2 <= (double)D;
+            const bool accept = e2 <= (R)D;
             double hnext;
-            if (e2 < 1.7976931348623157e308) {  // finite (false for NaN and Inf)
-                hnext = step * tr.pi.step(e2 * (1.0 / D), accept);
+            if (e2 < (sizeof(R) == 4 ? (R)3.4028234e38f : (R)1.7976931348623157e308)) {  // finite (false for NaN and Inf)
+                hnext = step * (double)tr.pi.step((float)(e2 * (R)(1.0 / D)), accept);
             } else {
                 // trial step left the domain of F/R: reject with the maximal shrink (what
                 // OrdinaryDiffEq does with an infinite estimate); fatal only if the accepted
@@ -581,6 +594,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG>::value) ensemble_kern
                 if (accept) {
 #pragma unroll
                     for (int i = 0; i < D; ++i) { tr.y[i] = yn[i]; tr.k1[i] = k7[i]; }
+                    if constexpr (T::SHADOW_T) { tr.tacc += (double)inc; tr.y[D - 1] = (R)tr.tacc; }
                     // tstop reached: exactly (clipped step) or within 100 eps (OrdinaryDiffEq's
                     // floating-point snap; here step < rem, so the gap is rem - step)
                     double sn = tr.s + step;
@@ -626,11 +640,11 @@ struct ModelEntry {
     pdmp_model_info info;
     int rec_words;  // RecLayout::WORDS
     int sched_jump, sched_refill;  // SchedDefaults<M>
-    // launch(alg, ode, records, stats, P, grid, smem, stream): returns cudaError_t
-    cudaError_t (*launch)(int alg, int ode, bool records, bool stats, const KParams& P, int grid, size_t smem,
+    // launch(alg, ode, precision, records, stats, P, grid, smem, stream): returns cudaError_t
+    cudaError_t (*launch)(int alg, int ode, int prec, bool records, bool stats, const KParams& P, int grid, size_t smem,
                           cudaStream_t stream);
     // occupancy: resident CTAs per SM for that variant
-    cudaError_t (*occupancy)(int alg, int ode, bool records, bool stats, size_t smem, int* blocks_per_sm);
+    cudaError_t (*occupancy)(int alg, int ode, int prec, bool records, bool stats, size_t smem, int* blocks_per_sm);
     // compaction pool -> CSR
     cudaError_t (*compact)(const KParams& P, const unsigned long long* offsets, double* time, double* xc,
                            void* xd, int xd_bytes, cudaStream_t stream);
@@ -685,30 +699,33 @@ __global__ void __launch_bounds__(128, 16) compact_kernel(const KParams P, const
 }
 
 // calls f(kernel function pointer) for the requested variant
-template <class M, class Tab, int ALG, class Fn>
+template <class M, class Tab, int ALG, class R, class Fn>
 cudaError_t with_variant(bool records, bool stats, Fn&& f) {
-    if (records && stats) return f(ensemble_kernel<M, Tab, ALG, true, true>);
-    if (records) return f(ensemble_kernel<M, Tab, ALG, true, false>);
-    if (stats) return f(ensemble_kernel<M, Tab, ALG, false, true>);
-    return f(ensemble_kernel<M, Tab, ALG, false, false>);
+    if (records && stats) return f(ensemble_kernel<M, Tab, ALG, true, true, R>);
+    if (records) return f(ensemble_kernel<M, Tab, ALG, true, false, R>);
+    if (stats) return f(ensemble_kernel<M, Tab, ALG, false, true, R>);
+    return f(ensemble_kernel<M, Tab, ALG, false, false, R>);
+}
+template <class M, int ALG, class Fn>
+cudaError_t with_alg_variant(int ode, int prec, bool records, bool stats, Fn&& f) {
+    if (prec == PDMP_PREC_FP32) {
+        return ode == PDMP_ODE_TSIT5 ? with_variant<M, TabTsit5, ALG, float>(records, stats, f)
+                                     : with_variant<M, TabDP5, ALG, float>(records, stats, f);
+    }
+    return ode == PDMP_ODE_TSIT5 ? with_variant<M, TabTsit5, ALG, double>(records, stats, f)
+                                 : with_variant<M, TabDP5, ALG, double>(records, stats, f);
 }
 template <class M, class Fn>
-cudaError_t with_model_variant(int alg, int ode, bool records, bool stats, Fn&& f) {
-    if (alg == PDMP_ALG_CHV) {
-        return ode == PDMP_ODE_TSIT5 ? with_variant<M, TabTsit5, PDMP_ALG_CHV>(records, stats, f)
-                                     : with_variant<M, TabDP5, PDMP_ALG_CHV>(records, stats, f);
-    }
-    if constexpr (M::HAS_BOUND) {
-        return ode == PDMP_ODE_TSIT5 ? with_variant<M, TabTsit5, PDMP_ALG_REJECTION>(records, stats, f)
-                                     : with_variant<M, TabDP5, PDMP_ALG_REJECTION>(records, stats, f);
-    }
+cudaError_t with_model_variant(int alg, int ode, int prec, bool records, bool stats, Fn&& f) {
+    if (alg == PDMP_ALG_CHV) return with_alg_variant<M, PDMP_ALG_CHV>(ode, prec, records, stats, f);
+    if constexpr (M::HAS_BOUND) return with_alg_variant<M, PDMP_ALG_REJECTION>(ode, prec, records, stats, f);
     return cudaErrorInvalidValue;
 }
 
 template <class M>
-cudaError_t model_launch(int alg, int ode, bool records, bool stats, const KParams& P, int grid, size_t smem,
+cudaError_t model_launch(int alg, int ode, int prec, bool records, bool stats, const KParams& P, int grid, size_t smem,
                          cudaStream_t st) {
-    return with_model_variant<M>(alg, ode, records, stats, [&](auto kern) {
+    return with_model_variant<M>(alg, ode, prec, records, stats, [&](auto kern) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -718,8 +735,8 @@ cudaError_t model_launch(int alg, int ode, bool records, bool stats, const KPara
     });
 }
 template <class M>
-cudaError_t model_occupancy(int alg, int ode, bool records, bool stats, size_t smem, int* out) {
-    return with_model_variant<M>(alg, ode, records, stats, [&](auto kern) {
+cudaError_t model_occupancy(int alg, int ode, int prec, bool records, bool stats, size_t smem, int* out) {
+    return with_model_variant<M>(alg, ode, prec, records, stats, [&](auto kern) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;

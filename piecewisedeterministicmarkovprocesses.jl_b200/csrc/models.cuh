@@ -10,14 +10,18 @@
 //     rates(r, x, xd, p, t)         all NR rates            (R(rate, xc, xd, parms, t, false))
 //     bound(x, xd, p, t)            rate bound              (R(...)[2], Rejection only)
 //     delta(x, xd, p, t, ev)        jump on xc after nu     (Delta(xc, xd, parms, t, ind_reaction), ev 1-based)
+//   Every functor is a template on the real type R (double; float for the optional FP32 kernels):
+//   state arrays and time are R, parameters stay `const double* p` (cast with R(p[i])), and
+//   literals are written R(...) so that the FP32 kernels never promote to double.
 //   optional fast path (HAS_CHV_FIELD): chv_field(dy, y, xd, p) = (F, 1) / rtot written out
 //   algebraically, saving the reciprocal when the model allows it.
 // x is indexable 0..NC-1 (the CHV kernel passes the extended state, time in slot NC, exactly
 // like the reference passes `x` with the time slot to R and F: src/chvdiffeq.jl:6-16).
 // xd is int32 in registers; the reference's Int64 is restored on output.
 //
-// USER MODELS: write such a struct in a header, add it to PDMP_MODEL_LIST in registry.cuh and
-// rebuild (python -c "import __graft_entry__ as g; g.build()").  See INTEGRATION.md.
+// USER MODELS: write such a struct here, add csrc/inst_<name>.cu (make_entry<YourDev>), list it in
+// registry() at the top of abi.cu and rebuild (python -c "import __graft_entry__ as g; g.build()").
+// See INTEGRATION.md.
 #pragma once
 #include "device_core.cuh"
 
@@ -28,19 +32,19 @@ struct TcpDev {  // examples/tcp.jl:25-45
     static constexpr bool HAS_BOUND = true, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = true;
     static constexpr const char* NAME = "tcp";
     static constexpr int SCHED_JUMP = 16, SCHED_REFILL = 2;   // ~5.5 cheap RK attempts per jump
-    PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) {
-        dx[0] = (xd[0] & 1) ? -1.0 : 1.0;  // mod(xd[1], 2) == 0 ? 1 : -1
+    template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
+        dx[0] = (xd[0] & 1) ? R(-1) : R(1);  // mod(xd[1], 2) == 0 ? 1 : -1
     }
-    PDMP_DEV static double rtot(const double* x, const int* xd, const double* p, double t) { return rcp_fast(x[0]); }
-    PDMP_DEV static void rates(double* r, const double* x, const int* xd, const double* p, double t) {
-        r[0] = 1.0 / x[0];
-        r[1] = 0.0;
+    template <class R> PDMP_DEV static R rtot(const R* x, const int* xd, const double* p, R t) { return rcp_fast(x[0]); }
+    template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
+        r[0] = R(1) / x[0];
+        r[1] = R(0);
     }
-    PDMP_DEV static double bound(const double* x, const int* xd, const double* p, double t) { return 100.0; }
-    PDMP_DEV static void delta(double* x, int* xd, const double* p, double t, int ev) {}
+    template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(100); }
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
     // (F, 1) / (1/x) = (±x, x)
-    PDMP_DEV static void chv_field(double* dy, const double* y, const int* xd, const double* p) {
-        const double sg = (double)(1 - 2 * (xd[0] & 1));  // hoisted out of the stage loop by the compiler
+    template <class R> PDMP_DEV static void chv_field(R* dy, const R* y, const int* xd, const double* p) {
+        const R sg = (R)(1 - 2 * (xd[0] & 1));  // hoisted out of the stage loop by the compiler
         dy[0] = sg * y[0];
         dy[1] = y[0];
     }
@@ -51,19 +55,19 @@ struct Tcp2dDev {  // examples/tcp2d.jl:4-25
     static constexpr bool HAS_BOUND = false, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;
     static constexpr const char* NAME = "tcp2d";
     static constexpr int SCHED_JUMP = 16, SCHED_REFILL = 8;   // short trajectories: batch the initialisations
-    PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) {
-        if ((xd[0] & 1) == 0) { dx[0] = 1.0; dx[1] = -1.0 * x[1]; }
-        else { dx[0] = -1.0 * x[0]; dx[1] = 1.0; }
+    template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
+        if ((xd[0] & 1) == 0) { dx[0] = R(1); dx[1] = R(-1) * x[1]; }
+        else { dx[0] = R(-1) * x[0]; dx[1] = R(1); }
     }
-    PDMP_DEV static double rtot(const double* x, const int* xd, const double* p, double t) {
-        return (x[0] + x[1]) + p[0] * (double)xd[0] * x[0];
+    template <class R> PDMP_DEV static R rtot(const R* x, const int* xd, const double* p, R t) {
+        return (x[0] + x[1]) + R(p[0]) * (R)xd[0] * x[0];
     }
-    PDMP_DEV static void rates(double* r, const double* x, const int* xd, const double* p, double t) {
+    template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
         r[0] = x[0] + x[1];
-        r[1] = p[0] * (double)xd[0] * x[0];
+        r[1] = R(p[0]) * (R)xd[0] * x[0];
     }
-    PDMP_DEV static double bound(const double* x, const int* xd, const double* p, double t) { return 0.0; }
-    PDMP_DEV static void delta(double* x, int* xd, const double* p, double t, int ev) {}
+    template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(0); }
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
 };
 
 struct MorrisLecarDev {  // examples/morris_lecar.jl:8-28
@@ -72,23 +76,23 @@ struct MorrisLecarDev {  // examples/morris_lecar.jl:8-28
     static constexpr const char* NAME = "morris_lecar";
     static constexpr int SCHED_JUMP = 6, SCHED_REFILL = 2;    // ~2 expensive RK attempts (18 exp) per jump
     enum { v_Na, g_Na, v_K, g_K, v_L, g_L, I_app, gamma_na, k_na, beta_na, gamma_k, k_k, beta_k, M, N };
-    PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) {
-        dx[0] = (double)xd[1] / p[N] * (p[g_Na] * (p[v_Na] - x[0])) +
-                (double)xd[3] / p[M] * (p[g_K] * (p[v_K] - x[0])) + (p[g_L] * (p[v_L] - x[0])) + p[I_app];
+    template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
+        dx[0] = (R)xd[1] / R(p[N]) * (R(p[g_Na]) * (R(p[v_Na]) - x[0])) +
+                (R)xd[3] / R(p[M]) * (R(p[g_K]) * (R(p[v_K]) - x[0])) + (R(p[g_L]) * (R(p[v_L]) - x[0])) + R(p[I_app]);
     }
-    PDMP_DEV static void rates(double* r, const double* x, const int* xd, const double* p, double t) {
-        r[0] = p[beta_na] * exp(4.0 * p[gamma_na] * x[0] + 4.0 * p[k_na]) * (double)xd[0];
-        r[1] = p[beta_na] * (double)xd[1];
-        r[2] = p[beta_k] * exp(p[gamma_k] * x[0] + p[k_k]) * (double)xd[2];
-        r[3] = p[beta_k] * exp(-p[gamma_k] * x[0] - p[k_k]) * (double)xd[3];
+    template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
+        r[0] = R(p[beta_na]) * exp(R(4) * R(p[gamma_na]) * x[0] + R(4) * R(p[k_na])) * (R)xd[0];
+        r[1] = R(p[beta_na]) * (R)xd[1];
+        r[2] = R(p[beta_k]) * exp(R(p[gamma_k]) * x[0] + R(p[k_k])) * (R)xd[2];
+        r[3] = R(p[beta_k]) * exp(-R(p[gamma_k]) * x[0] - R(p[k_k])) * (R)xd[3];
     }
-    PDMP_DEV static double rtot(const double* x, const int* xd, const double* p, double t) {
-        double r[4];
+    template <class R> PDMP_DEV static R rtot(const R* x, const int* xd, const double* p, R t) {
+        R r[4];
         rates(r, x, xd, p, t);
         return ((r[0] + r[1]) + r[2]) + r[3];
     }
-    PDMP_DEV static double bound(const double* x, const int* xd, const double* p, double t) { return 0.0; }
-    PDMP_DEV static void delta(double* x, int* xd, const double* p, double t, int ev) {}
+    template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(0); }
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
 };
 
 template <bool REJ>
@@ -96,19 +100,19 @@ struct SirDevT {  // examples/sir-rejection.jl:3-17 (REJ) / examples/sir.jl:6-27
     static constexpr int NC = 1, ND = 4, NR = 3, NP = 2;
     static constexpr bool HAS_BOUND = REJ, HAS_DELTA = false, ZERO_FLOW = true, HAS_CHV_FIELD = false;
     static constexpr const char* NAME = REJ ? "sir_rejection" : "sir";
-    PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) { dx[0] = 0.0; }
-    PDMP_DEV static void rates(double* r, const double* x, const int* xd, const double* p, double t) {
-        r[0] = p[0] * (double)xd[0] * (double)xd[1];
-        r[1] = p[1] * (double)xd[1];
-        r[2] = REJ ? p[0] : 0.01;
+    template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) { dx[0] = R(0); }
+    template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
+        r[0] = R(p[0]) * (R)xd[0] * (R)xd[1];
+        r[1] = R(p[1]) * (R)xd[1];
+        r[2] = REJ ? R(p[0]) : R(0.01);
     }
-    PDMP_DEV static double rtot(const double* x, const int* xd, const double* p, double t) {
-        double r[3];
+    template <class R> PDMP_DEV static R rtot(const R* x, const int* xd, const double* p, R t) {
+        R r[3];
         rates(r, x, xd, p, t);
         return r[0] + r[1] + r[2];
     }
-    PDMP_DEV static double bound(const double* x, const int* xd, const double* p, double t) { return p[0] + 3.5; }
-    PDMP_DEV static void delta(double* x, int* xd, const double* p, double t, int ev) {}
+    template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(p[0] + 3.5); }
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
 };
 using SirRejDev = SirDevT<true>;
 using SirChvDev = SirDevT<false>;
@@ -117,72 +121,72 @@ struct StiffDev {  // test/pdmpStiff.jl:71-90
     static constexpr int NC = 1, ND = 2, NR = 2, NP = 1;
     static constexpr bool HAS_BOUND = true, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;
     static constexpr const char* NAME = "pdmp_stiff";
-    PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) {
-        dx[0] = (xd[0] & 1) ? -3.0 * (x[0] * x[0]) : 10.0 * x[0];
+    template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
+        dx[0] = (xd[0] & 1) ? R(-3) * (x[0] * x[0]) : R(10) * x[0];
     }
-    PDMP_DEV static double rtot(const double* x, const int* xd, const double* p, double t) { return x[0] + p[0]; }
-    PDMP_DEV static void rates(double* r, const double* x, const int* xd, const double* p, double t) {
+    template <class R> PDMP_DEV static R rtot(const R* x, const int* xd, const double* p, R t) { return x[0] + R(p[0]); }
+    template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
         r[0] = x[0];
-        r[1] = p[0];
+        r[1] = R(p[0]);
     }
-    PDMP_DEV static double bound(const double* x, const int* xd, const double* p, double t) { return p[0] + 100.0; }
-    PDMP_DEV static void delta(double* x, int* xd, const double* p, double t, int ev) {}
+    template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(p[0] + 100.0); }
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
 };
 
 struct TcpRejDev {  // examples/tcp_rejection.jl:5-25
     static constexpr int NC = 1, ND = 2, NR = 2, NP = 1;
     static constexpr bool HAS_BOUND = true, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;
     static constexpr const char* NAME = "tcp_rejection";
-    PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) {
-        dx[0] = (xd[0] & 1) ? -10.0 * x[0] : 1.0;
+    template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
+        dx[0] = (xd[0] & 1) ? R(-10) * x[0] : R(1);
     }
-    PDMP_DEV static double rtot(const double* x, const int* xd, const double* p, double t) {
-        return 1.0 / (1.0 + exp(-x[0]));
+    template <class R> PDMP_DEV static R rtot(const R* x, const int* xd, const double* p, R t) {
+        return R(1) / (R(1) + exp(-x[0]));
     }
-    PDMP_DEV static void rates(double* r, const double* x, const int* xd, const double* p, double t) {
-        r[0] = 1.0 / (1.0 + exp(-x[0]));
-        r[1] = 0.0;
+    template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
+        r[0] = R(1) / (R(1) + exp(-x[0]));
+        r[1] = R(0);
     }
-    PDMP_DEV static double bound(const double* x, const int* xd, const double* p, double t) { return 1.0; }
-    PDMP_DEV static void delta(double* x, int* xd, const double* p, double t, int ev) {}
+    template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(1); }
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
 };
 
 struct ExplosionDev {  // examples/pdmpExplosion.jl:29-45, r = 10
     static constexpr int NC = 1, ND = 2, NR = 2, NP = 1;
     static constexpr bool HAS_BOUND = true, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;
     static constexpr const char* NAME = "pdmp_explosion";
-    PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) {
-        dx[0] = -10.0 * (double)(2 * (xd[0] & 1) - 1) * x[0];
+    template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
+        dx[0] = R(-10) * (R)(2 * (xd[0] & 1) - 1) * x[0];
     }
-    PDMP_DEV static double rtot(const double* x, const int* xd, const double* p, double t) { return x[0]; }
-    PDMP_DEV static void rates(double* r, const double* x, const int* xd, const double* p, double t) {
+    template <class R> PDMP_DEV static R rtot(const R* x, const int* xd, const double* p, R t) { return x[0]; }
+    template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
         r[0] = x[0];
-        r[1] = 0.0;
+        r[1] = R(0);
     }
-    PDMP_DEV static double bound(const double* x, const int* xd, const double* p, double t) { return 40.0; }
-    PDMP_DEV static void delta(double* x, int* xd, const double* p, double t, int ev) {}
+    template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(40); }
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
 };
 
 struct NeuronEvaDev {  // examples/pdmp_example_eva.jl:5-45 (Delta resets xc on reaction 2)
     static constexpr int NC = 1, ND = 2, NR = 3, NP = 1;
     static constexpr bool HAS_BOUND = true, HAS_DELTA = true, ZERO_FLOW = false, HAS_CHV_FIELD = false;
     static constexpr const char* NAME = "neuron_eva";
-    PDMP_DEV static void F(double* dx, const double* x, const int* xd, const double* p, double t) {
-        dx[0] = -(x[0] - 1.5);
+    template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
+        dx[0] = -(x[0] - R(1.5));
     }
-    PDMP_DEV static double rtot(const double* x, const int* xd, const double* p, double t) {
-        const double x2 = x[0] * x[0];
-        return xd[0] == 0 ? x2 * x2 + p[0] : 1.0 + p[0];
+    template <class R> PDMP_DEV static R rtot(const R* x, const int* xd, const double* p, R t) {
+        const R x2 = x[0] * x[0];
+        return xd[0] == 0 ? x2 * x2 + R(p[0]) : R(1) + R(p[0]);
     }
-    PDMP_DEV static void rates(double* r, const double* x, const int* xd, const double* p, double t) {
-        const double x2 = x[0] * x[0];
-        if (xd[0] == 0) { r[0] = x2 * x2; r[1] = 0.0; }
-        else { r[0] = 0.0; r[1] = 1.0; }
-        r[2] = p[0];
+    template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
+        const R x2 = x[0] * x[0];
+        if (xd[0] == 0) { r[0] = x2 * x2; r[1] = R(0); }
+        else { r[0] = R(0); r[1] = R(1); }
+        r[2] = R(p[0]);
     }
-    PDMP_DEV static double bound(const double* x, const int* xd, const double* p, double t) { return 5.0; }
-    PDMP_DEV static void delta(double* x, int* xd, const double* p, double t, int ev) {
-        if (ev == 2) x[0] = 0.0;
+    template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(5); }
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {
+        if (ev == 2) x[0] = R(0);
     }
 };
 

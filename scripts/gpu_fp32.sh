@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -q -m gpu --timeout 900 2>&1 | tail -15
+run() { "$@" 2>&1 | tail -1 | sed -E "s/\{.*'kernel_ms'/kernel_ms/"; }
+PDMP_TSTOP_POLICY=1 run python scripts/profile_run.py tcp 4194304
+PDMP_PREC=fp32 PDMP_TSTOP_POLICY=1 run python scripts/profile_run.py tcp 4194304
+run python scripts/profile_run.py tcp2d 2097152
+PDMP_PREC=fp32 run python scripts/profile_run.py tcp2d 2097152
+run python scripts/profile_run.py morris_lecar 1048576
+PDMP_PREC=fp32 run python scripts/profile_run.py morris_lecar 1048576

@@ -11,18 +11,20 @@ import pdmp_b200 as P
 model = sys.argv[1] if len(sys.argv) > 1 else "tcp"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 pol = int(os.environ.get("PDMP_TSTOP_POLICY", "0"))
+prec = os.environ.get("PDMP_PREC", "fp64")
+tol = dict(reltol=1e-5, abstol=1e-7) if prec == "fp32" else {}
 if model == "tcp":
     pb = P.models.problem("tcp", tspan=(0.0, 200.0))
     xc0 = 0.5 + np.random.default_rng(2024).random((n, 1))
-    ens = P.Ensemble(pb, P.CHVGPU("tcp"), trajectories=n, n_jumps=1000, sample_times=[50.0, 100.0, 150.0, 200.0],
-                     max_records=n * 160, xc0=xc0, tstop_policy=pol)
+    ens = P.Ensemble(pb, P.CHVGPU("tcp", precision=prec), trajectories=n, n_jumps=1000, sample_times=[50.0, 100.0, 150.0, 200.0],
+                     max_records=n * 160, xc0=xc0, tstop_policy=pol, **tol)
 elif model == "morris_lecar":
     pb = P.models.problem("morris_lecar")
-    ens = P.Ensemble(pb, P.CHVGPU("morris_lecar"), trajectories=n, n_jumps=2200, max_records=n * 800)
+    ens = P.Ensemble(pb, P.CHVGPU("morris_lecar", precision=prec), trajectories=n, n_jumps=2200, max_records=n * 800, **tol)
 elif model == "tcp2d":
     pb = P.models.problem("tcp2d", tspan=(0.0, 10.0))
-    ens = P.Ensemble(pb, P.CHVGPU("tcp2d"), trajectories=n, n_jumps=2000, no_records=True,
-                     sample_times=list(10.0 * np.arange(1, 17) / 16), hist=[(0, 0.0, 4.0), (1, 0.0, 4.0)], hist_bins=256)
+    ens = P.Ensemble(pb, P.CHVGPU("tcp2d", precision=prec), trajectories=n, n_jumps=2000, no_records=True,
+                     sample_times=list(10.0 * np.arange(1, 17) / 16), hist=[(0, 0.0, 4.0), (1, 0.0, 4.0)], hist_bins=256, **tol)
 elif model == "sir_rejection":
     pb = P.models.problem("sir_rejection")
     ens = P.Ensemble(pb, P.RejectionGPU("sir_rejection"), trajectories=n, n_jumps=1000, max_records=n * 260)

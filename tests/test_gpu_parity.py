@@ -444,3 +444,42 @@ def test_run_is_ordered_on_the_callers_stream(G):
         want = np.concatenate([res.stat_count.ravel(), res.stat_sum.ravel(), res.stat_sumsq.ravel()])
         assert np.array_equal(snap.cpu().numpy(), want)
     ens.close()
+
+
+# ---- optional FP32 kernels (north star: "FP64 (FP32 optional)") ---------------------------------
+
+def test_fp32_closed_form_and_fp64_agreement(G, golden):
+    # stage arithmetic in float, time-like scalars in double: known answers to FP32-level tolerances
+    pb = G.models.problem("tcp")
+    r = G.solve(pb, G.CHVGPU("tcp", precision="fp32"), n_jumps=10, replay=golden["tcp10_u"], reltol=1e-5, abstol=1e-7)
+    assert len(r.time) == 10 and np.array_equal(r.xd[:, 0], golden["tcp10_xd"])
+    assert np.max(np.abs(r.time - golden["tcp10_t"]) / np.maximum(golden["tcp10_t"], 1.0)) < 2e-4   # reference bar: 1e-4 abs at tf=1e5
+    r = G.solve(pb, G.CHVGPU("tcp", precision="fp32"), n_jumps=700, replay=golden["tcp700_u"], reltol=1e-5, abstol=1e-7)
+    assert np.array_equal(r.xd[:, 0], golden["tcp700_xd"])
+    assert relerr(r.time, golden["tcp700_t"]) < 1e-3
+    st = G.models.problem("pdmp_stiff")
+    r = G.solve(st, G.CHVGPU("pdmp_stiff", precision="fp32"), n_jumps=50, replay=golden["stiff_u"], reltol=1e-5, abstol=1e-7)
+    assert relerr(r.time, golden["stiff_t"]) < 2e-3          # e^(10 S) growth amplifies the FP32 round-off
+    rj = G.models.problem("tcp_rejection")
+    r = G.solve(rj, G.RejectionGPU("tcp_rejection", precision="fp32"), n_jumps=50, replay=golden["tcprej_u"], reltol=1e-5, abstol=1e-7)
+    assert np.array_equal(r.xd[:50, 0], golden["tcprej_xd"]) and r.nrejected[0] == int(golden["tcprej_nrej"][0])
+    assert np.max(np.abs(r.xc[:50, 0] - golden["tcprej_x"])) < 1e-3
+
+
+# (not TCP: log x does a random walk, so a sizeable fraction of paths leaves the FLOAT range —
+#  x underflows to 0, rate 1/x = inf — and is flagged NO_PROGRESS about 8x more often than in FP64)
+@pytest.mark.parametrize("model,tf,nj", [("tcp2d", 10.0, 2000), ("morris_lecar", 50.0, 2200)])
+def test_fp32_moments_match_fp64(G, model, tf, nj):
+    pb = G.models.problem(model)
+    pb.tspan[1] = tf
+    st = np.linspace(tf / 8, tf, 8)
+    kw = dict(trajectories=300_000, n_jumps=nj, sample_times=st, no_records=True)
+    a = G.solve(pb, G.CHVGPU(model), seed=21, **kw)
+    b = G.solve(pb, G.CHVGPU(model, precision="fp32"), seed=22, reltol=1e-5, abstol=1e-7, **kw)
+    assert b.status_histogram().get("OK", 0) + b.status_histogram().get("HIT_NJUMPS", 0) > 0.999 * 300_000
+    bad_mean, bad_var = _ci_check(b, a)
+    assert not bad_mean.any(), (b.mean()[bad_mean], a.mean()[bad_mean])
+    assert not bad_var.any(), (b.var()[bad_var], a.var()[bad_var])
+    # same Philox stream, FP32 vs FP64: the bulk of the trajectories follows the same discrete path
+    c = G.solve(pb, G.CHVGPU(model, precision="fp32"), seed=21, reltol=1e-5, abstol=1e-7, **kw)
+    assert np.mean(c.njumps == a.njumps) > 0.95
