@@ -258,6 +258,12 @@ def run_gpu(args):
     value = float(tot[0].item()) / (ms_max * 1e-3)
     traj_per_s = float(tot[1].item()) / (ms_max * 1e-3)
 
+    # how the trajectories of the last step ended (by tf vs by the n_jumps cap)
+    fin = ens.fetch(records=False)
+    status_hist = fin.status_histogram()
+    mean_jumps = float(fin.njumps.mean() - 1)
+    del fin
+
     # ---- end to end through the host-buffer API (H2D ICs, step, D2H of everything) ----
     # the pinned host staging holds every record of a step (~51 GB at 10^7 trajectories): bound it
     # by the host memory actually available to this rank
@@ -309,6 +315,7 @@ def run_gpu(args):
             "trajectories_per_sec": traj_per_s,
             "jumps_per_step_rank0": jumps / args.steps, "records_per_step_rank0": records / args.steps,
             "rk_attempts_per_jump": attempts / max(jumps, 1),
+            "status_rank0_last_step": status_hist, "mean_jumps_per_trajectory": mean_jumps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ics_e.nbytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps, "trajectories_per_gpu": n_e2e,
                     "ms_per_step": 1e3 * float(e.item()) / e2e_steps},

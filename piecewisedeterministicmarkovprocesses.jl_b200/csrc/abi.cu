@@ -484,6 +484,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
     CK(cudaEventRecord(e->ev_kbeg, e->cs[0]));
     // resident runs over a shared pool are ONE persistent kernel; host-mode runs (and runs whose
     // pools are per-stream) are chunked so that compaction / D2H of chunk k overlap chunk k+1
+    // (measured: chunking a resident run costs 5 % at 4 chunks and 19 % at 10 — every chunk has its own tail)
     const int nch = (!host_mode && e->shared_pool) ? 1 : e->n_chunks;
     const unsigned long long chn = nch == 1 ? std::max<unsigned long long>(e->n, 1) : e->chunk_n;
     e->cur_chunks = nch; e->cur_chunk_n = chn;
