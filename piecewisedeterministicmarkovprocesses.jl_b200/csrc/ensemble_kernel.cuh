@@ -457,12 +457,14 @@ struct Traj {
 };
 
 // resident CTAs per SM the kernel is compiled for: small models fit 6 x 128 threads in the
-// register file (<= 80 registers), the larger ones 4 (<= 128 registers)
+// register file (<= 80 registers), medium ones 5 (<= 96), the larger ones 4 (<= 128 registers;
+// Morris-Lecar loses 10 % to spills at 96)
 template <class M, int ALG, class R>
 struct MinBlocks {
     static constexpr int D = (ALG == PDMP_ALG_CHV) ? M::NC + 1 : M::NC;
     static constexpr bool small = (D <= 2 && M::NR <= 2 && M::ND <= 2);
-    static constexpr int value = sizeof(R) == 4 ? (small ? 7 : 5) : (small ? 6 : 4);
+    static constexpr bool medium = (D <= 3 && M::NR <= 2 && M::ND <= 2);   // tcp2d: 96 registers, measured +8 %
+    static constexpr int value = sizeof(R) == 4 ? (small ? 7 : 5) : (small ? 6 : medium ? 5 : 4);
 };
 
 // lane states of the phase scheduler
