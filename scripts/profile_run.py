@@ -17,7 +17,7 @@ if model == "tcp":
     pb = P.models.problem("tcp", tspan=(0.0, 200.0))
     xc0 = 0.5 + np.random.default_rng(2024).random((n, 1))
     ens = P.Ensemble(pb, P.CHVGPU("tcp", precision=prec), trajectories=n, n_jumps=1000, sample_times=[50.0, 100.0, 150.0, 200.0],
-                     max_records=n * 160, xc0=xc0, tstop_policy=pol, **tol)
+                     max_records=n * 160, xc0=xc0, tstop_policy=pol, xd_transport="auto", **tol)
 elif model == "morris_lecar":
     pb = P.models.problem("morris_lecar")
     ens = P.Ensemble(pb, P.CHVGPU("morris_lecar", precision=prec), trajectories=n, n_jumps=2200, max_records=n * 800, **tol)
