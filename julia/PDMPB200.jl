@@ -36,7 +36,8 @@ device).  `ode` is `:dp5` (Dormand-Prince 5(4)) or `:tsit5`.
 struct CHVGPU <: PDMP.AbstractCHV
     model::Symbol
     ode::Symbol
-    CHVGPU(model; ode = :dp5) = new(Symbol(model), ode)
+    precision::Symbol     # :fp64 (default) or :fp32 (float state and stage arithmetic, double time)
+    CHVGPU(model; ode = :dp5, precision = :fp64) = new(Symbol(model), ode, precision)
 end
 
 """
@@ -48,12 +49,14 @@ Ensemble thinning with the model's rate bound; replaces `Rejection(Tsit5())`
 struct RejectionGPU <: PDMP.AbstractRejection
     model::Symbol
     ode::Symbol
-    RejectionGPU(model; ode = :dp5) = new(Symbol(model), ode)
+    precision::Symbol
+    RejectionGPU(model; ode = :dp5, precision = :fp64) = new(Symbol(model), ode, precision)
 end
 
 algorithm_code(::CHVGPU) = Int32(0)        # PDMP_ALG_CHV
 algorithm_code(::RejectionGPU) = Int32(1)  # PDMP_ALG_REJECTION
 ode_code(a) = a.ode === :tsit5 ? Int32(1) : a.ode === :dp5 ? Int32(0) : error("ode must be :dp5 or :tsit5")
+precision_code(a) = a.precision === :fp32 ? Int32(1) : a.precision === :fp64 ? Int32(0) : error("precision must be :fp64 or :fp32")
 
 # ---- C structs (include/pdmp_b200.h) -------------------------------------------------------
 struct ModelInfo
@@ -264,7 +267,7 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
                       isempty(ru) ? C_NULL : pointer(ru), isempty(ru) ? 0 : size(ru, 1),
                       isempty(st) ? C_NULL : pointer(st), isempty(hc) ? C_NULL : pointer(hc),
                       isempty(hlo) ? C_NULL : pointer(hlo), isempty(hhi) ? C_NULL : pointer(hhi), maxrec,
-                      algorithm_code(algo), ode_code(algo), 0, isempty(ru) ? 0 : 1,
+                      algorithm_code(algo), ode_code(algo), precision_code(algo), isempty(ru) ? 0 : 1,
                       save_positions[1], save_positions[2], no_records, length(st), length(hc),
                       isempty(hc) ? 0 : hist_bins, device, tstop_policy, 0, xd_bytes)
         end
