@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PDMP_ABI_VERSION 5
+#define PDMP_ABI_VERSION 6
 
 /* ---- enumerations ------------------------------------------------------------------ */
 
@@ -111,7 +111,12 @@ typedef struct pdmp_problem_desc {
     int32_t xd0_per_traj;
     int32_t nu_col_major;     /* Julia passes column-major matrices                        */
     int32_t n_parms;
-    int32_t reserved0;
+    int32_t rate_kind;        /* 0: VariableRate (reference default, src/problem.jl:55)
+                                 1: ConstantRate (src/rate.jl:17-40): the total rate is constant
+                                    between jumps; the CHV field re-uses the value computed at the
+                                    post-jump state instead of re-evaluating R at every stage.
+                                    Only for models whose rates depend on xd alone
+                                    (PDMP_ERR_UNSUPPORTED otherwise: it would change results)   */
 } pdmp_problem_desc;
 
 /* Mirrors the keyword arguments of the reference `solve` (src/chvdiffeq.jl:187-219,

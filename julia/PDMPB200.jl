@@ -22,7 +22,7 @@ using Libdl
 
 export CHVGPU, RejectionGPU, EnsembleResult, device_count, list_models
 
-const ABI_VERSION = 5
+const ABI_VERSION = 6
 const libpdmp = Ref{String}(get(ENV, "PDMP_B200_LIB", "libpdmp_b200.so"))
 
 # ---- algorithm types ---------------------------------------------------------------------
@@ -85,7 +85,7 @@ struct ProblemDesc
     xd0_per_traj::Int32
     nu_col_major::Int32
     n_parms::Int32
-    reserved0::Int32
+    rate_kind::Int32
 end
 
 struct SolveOpts
@@ -261,7 +261,8 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
     GC.@preserve xc xd nu parms st hc hlo hhi ru begin
         desc = ProblemDesc(trajectories, traj_id_offset, pointer(xc), pointer(xd), pointer(nu),
                            isempty(parms) ? C_NULL : pointer(parms), problem.tspan[1], problem.tspan[2],
-                           info.id, xc0 === nothing ? 0 : 1, xd0 === nothing ? 0 : 1, 1, length(parms), 0)
+                           info.id, xc0 === nothing ? 0 : 1, xd0 === nothing ? 0 : 1, 1, length(parms),
+                           car.R isa PDMP.ConstantRate ? 1 : 0)   # ConstantRate wrapper (src/rate.jl:17-40)
         function opts(maxrec)
             SolveOpts(reltol, abstol, Int64(n_jumps), max_attempts, UInt64(seed),
                       isempty(ru) ? C_NULL : pointer(ru), isempty(ru) ? 0 : size(ru, 1),

@@ -203,6 +203,29 @@ struct ExplosionModel {  // examples/pdmpExplosion.jl:29-45 (r = 10)
     static void Delta(double*, int64_t*, const double*, double, int) {}
 };
 
+struct StiffDeltaModel {  // test/pdmpStiff.jl:198-215: the same model with the jumps written as a Delta! function
+    static constexpr int NC = 1, ND = 2, NR = 2, NP = 1;        // (PDMPProblem(F!, R!, Delta!, 2, ...): all-zero nu)
+    static constexpr bool HAS_BOUND = true, HAS_DELTA = true, ZERO_FLOW = false;
+    static constexpr const char* NAME = "pdmp_stiff_delta";
+    static void F(double* xdot, const double* xc, const int64_t* xd, const double* p, double t) { StiffModel::F(xdot, xc, xd, p, t); }
+    static void R(double* rate, const double* xc, const int64_t* xd, const double* p, double t, bool issum, double* out) {
+        StiffModel::R(rate, xc, xd, p, t, issum, out);
+    }
+    static void Delta(double*, int64_t* xd, const double*, double, int ev) {
+        if (ev == 1) xd[0] += 1; else xd[1] -= 1;
+    }
+};
+struct RatesCstModel {  // test/testRatesCst.jl:5-24 (rates constant between jumps)
+    static constexpr int NC = 1, ND = 2, NR = 2, NP = 1;
+    static constexpr bool HAS_BOUND = false, HAS_DELTA = false, ZERO_FLOW = false;
+    static constexpr const char* NAME = "rates_cst";
+    static void F(double* xdot, const double* xc, const int64_t* xd, const double* p, double t) { StiffModel::F(xdot, xc, xd, p, t); }
+    static void R(double* rate, const double*, const int64_t* xd, const double* p, double, bool issum, double* out) {
+        if (!issum) { rate[0] = 10.0 + (double)xd[0]; rate[1] = p[0]; out[0] = 0.0; out[1] = 0.0; }
+        else { out[0] = (10.0 + (double)xd[0]) + p[0]; out[1] = out[0]; }
+    }
+    static void Delta(double*, int64_t*, const double*, double, int) {}
+};
 struct NeuronEvaModel {  // examples/pdmp_example_eva.jl:5-45 (Delta acting on xc)
     static constexpr int NC = 1, ND = 2, NR = 3, NP = 1;
     static constexpr bool HAS_BOUND = true, HAS_DELTA = true, ZERO_FLOW = false;
@@ -881,7 +904,7 @@ void fill_info(int id, pdmp_model_info* out) {
     std::strncpy(out->name, M::NAME, sizeof(out->name) - 1);
 }
 
-constexpr int N_MODELS = 9;
+constexpr int N_MODELS = 11;
 
 template <class Fn>
 int dispatch_model(int id, Fn&& fn) {
@@ -895,6 +918,8 @@ int dispatch_model(int id, Fn&& fn) {
         case 6: return fn((TcpRejModel*)nullptr);
         case 7: return fn((ExplosionModel*)nullptr);
         case 8: return fn((NeuronEvaModel*)nullptr);
+        case 9: return fn((StiffDeltaModel*)nullptr);
+        case 10: return fn((RatesCstModel*)nullptr);
         default: g_err = "unknown model id"; return PDMP_ERR_MODEL;
     }
 }

@@ -9,9 +9,10 @@ does not load the CUDA library; the first solve does, and raises if it is missin
 from . import _abi, _marshal, distributed, models
 from .algorithms import (AbstractCHV, AbstractPDMPAlgorithm, AbstractRejection, CHVGPU, RejectionGPU)
 from .problem import EnsembleResult, PDMPProblem, PDMPResult
+from .rate import CompositeRate, ConstantRate, VariableRate
 from .solve import Ensemble, solve
 from ._lib import PDMPError, device_count, fp64_peak_tflops, list_models, model_info
 
 __all__ = ["PDMPProblem", "PDMPResult", "EnsembleResult", "CHVGPU", "RejectionGPU", "solve", "Ensemble",
            "models", "distributed", "PDMPError", "device_count", "fp64_peak_tflops", "list_models", "model_info",
-           "AbstractPDMPAlgorithm", "AbstractCHV", "AbstractRejection"]
+           "AbstractPDMPAlgorithm", "AbstractCHV", "AbstractRejection", "VariableRate", "ConstantRate", "CompositeRate"]

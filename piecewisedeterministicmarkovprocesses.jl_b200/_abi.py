@@ -1,11 +1,11 @@
-"""ctypes mirror of include/pdmp_b200.h (ABI version 5).
+"""ctypes mirror of include/pdmp_b200.h (ABI version 6).
 
 Pure declarations: no library is loaded here, so the oracle loader (oracle/oracle.py, test
 infrastructure) can share the struct layouts without touching the product library.
 """
 import ctypes as C
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 ALG_CHV, ALG_REJECTION = 0, 1
 ODE_DP5, ODE_TSIT5 = 0, 1
@@ -37,7 +37,7 @@ class ProblemDesc(C.Structure):
                 ("xc0", c_double_p), ("xd0", c_int64_p), ("nu", c_int64_p), ("parms", c_double_p),
                 ("t0", C.c_double), ("tf", C.c_double),
                 ("model_id", C.c_int32), ("xc0_per_traj", C.c_int32), ("xd0_per_traj", C.c_int32),
-                ("nu_col_major", C.c_int32), ("n_parms", C.c_int32), ("reserved0", C.c_int32)]
+                ("nu_col_major", C.c_int32), ("n_parms", C.c_int32), ("rate_kind", C.c_int32)]
 
 
 class SolveOpts(C.Structure):

@@ -62,6 +62,11 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
     d.model_id = info.id
     d.nu_col_major = 0
     d.n_parms = parms.size
+    kind = getattr(problem.R, "rate_kind", 0)     # rate.py wrappers; a bare R is a VariableRate (src/problem.jl:55)
+    if kind == 2:
+        raise NotImplementedError("CompositeRate needs a device functor split into a constant and a variable part; "
+                                  "use ConstantRate (rates depending on xd only) or the plain functor")
+    d.rate_kind = kind
 
     o = _abi.SolveOpts()
     o.reltol, o.abstol = float(reltol), float(abstol)

@@ -21,13 +21,15 @@
 namespace pdmp {
 // one translation unit per model (parallel nvcc), collected here
 ModelEntry entry_tcp(int), entry_tcp2d(int), entry_morris_lecar(int), entry_sir_rejection(int), entry_sir(int),
-    entry_pdmp_stiff(int), entry_tcp_rejection(int), entry_pdmp_explosion(int), entry_neuron_eva(int);
+    entry_pdmp_stiff(int), entry_tcp_rejection(int), entry_pdmp_explosion(int), entry_neuron_eva(int),
+    entry_pdmp_stiff_delta(int), entry_rates_cst(int);
 
 static const std::vector<ModelEntry>& registry() {
     static const std::vector<ModelEntry> r = {
         entry_tcp(0),           entry_tcp2d(1),         entry_morris_lecar(2),
         entry_sir_rejection(3), entry_sir(4),           entry_pdmp_stiff(5),
-        entry_tcp_rejection(6), entry_pdmp_explosion(7), entry_neuron_eva(8)};
+        entry_tcp_rejection(6), entry_pdmp_explosion(7), entry_neuron_eva(8),
+        entry_pdmp_stiff_delta(9), entry_rates_cst(10)};
     return r;
 }
 
@@ -210,6 +212,10 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
                                         std::to_string(m.info.n_parms) + " parameters");
     if (!d->xc0 || !d->xd0 || !d->nu || (!d->parms && d->n_parms)) return fail(PDMP_ERR_INVALID, "null problem array");
     if (o->algorithm != PDMP_ALG_CHV && o->algorithm != PDMP_ALG_REJECTION) return fail(PDMP_ERR_INVALID, "algorithm");
+    if (d->rate_kind != 0 && d->rate_kind != 1) return fail(PDMP_ERR_INVALID, "rate_kind");
+    if (d->rate_kind == 1 && !m.const_rate_ok)
+        return fail(PDMP_ERR_UNSUPPORTED, std::string("model '") + m.info.name + "' has rates that vary between jumps: "
+                                              "ConstantRate would change its results");
     if (o->algorithm == PDMP_ALG_REJECTION && !m.info.has_bound)
         return fail(PDMP_ERR_MODEL, std::string("model '") + m.info.name + "' has no rate bound: Rejection unavailable");
     if (o->ode != PDMP_ODE_DP5 && o->ode != PDMP_ODE_TSIT5) return fail(PDMP_ERR_INVALID, "ode");
@@ -258,6 +264,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
             P.nu[r * ND + c] = (int)v;
         }
     P.t0 = d->t0; P.tf = d->tf;
+    P.rate_const = d->rate_kind == 1;
     P.reltol = o->reltol; P.abstol = o->abstol;
     P.n_jumps = o->n_jumps;
     P.max_attempts = o->max_attempts > 0 ? o->max_attempts : 1000000ll;

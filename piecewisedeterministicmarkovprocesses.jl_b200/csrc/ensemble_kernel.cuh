@@ -35,6 +35,7 @@ struct KParams {
     double parms[MAXP];
     int nu[MAXR * MAXD];  // [r * ND + d]
     double t0, tf;
+    int rate_const;   // ConstantRate: the CHV field re-uses the total rate of the post-jump state
     // options
     double reltol, abstol;
     long long n_jumps, max_attempts;
@@ -77,6 +78,10 @@ struct RecLayout {
     static constexpr int BYTES = WORDS * 8;
 };
 
+// models whose rates depend on xd only may be run with the reference's ConstantRate wrapper
+template <class M, class = void> struct ConstRateOk { static constexpr bool value = false; };
+template <class M> struct ConstRateOk<M, decltype((void)M::CONST_RATE_OK)> { static constexpr bool value = M::CONST_RATE_OK; };
+
 // geometric segment sizes: segment k holds REC_BLOCK << (k >> 2) records (4 segments per doubling)
 __host__ __device__ inline unsigned seg_records(int k) { return (unsigned)REC_BLOCK << (k >> 2); }
 
@@ -95,6 +100,7 @@ struct Traj {
     R y[D];             // CHV: (xc, t) in the time-change variable s ; Rejection: xc in time t
     R k1[D];            // FSAL
     double tacc;        // SHADOW_T only: the time slot in double
+    R inv_rate;         // ConstantRate (src/rate.jl:17-40): 1 / total rate, cached from jump to jump
     double s, tstop, h; // integration variable, next threshold, proposed step
     PIController pi;
     // ---- PDMP state ----
@@ -127,7 +133,9 @@ struct Traj {
                 M::chv_field(dx, x, xd, P.parms);
             } else {
                 const R tau = x[NC];
-                const R inv = rcp_fast(M::rtot(x, xd, P.parms, tau));
+                R inv;
+                if constexpr (ConstRateOk<M>::value) inv = P.rate_const ? inv_rate : rcp_fast(M::rtot(x, xd, P.parms, tau));
+                else inv = rcp_fast(M::rtot(x, xd, P.parms, tau));
                 M::F(dx, x, xd, P.parms, tau);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) dx[i] *= inv;
@@ -136,6 +144,12 @@ struct Traj {
         } else {
             M::F(dx, x, xd, P.parms, t);  // Rejection flow, reference src/rejectiondiffeq.jl:5-8
         }
+    }
+
+    // ConstantRate: cr.totalrate is recomputed at the first call after a jump (src/rate.jl:28-33)
+    PDMP_DEV void refresh_rate(const KParams& P, double t) {
+        if constexpr (ConstRateOk<M>::value && ALG == PDMP_ALG_CHV)
+            if (P.rate_const) inv_rate = rcp_fast(M::rtot(y, xd, P.parms, (R)t));
     }
 
     // ---- record pool writer ----------------------------------------------------------
@@ -323,6 +337,7 @@ struct Traj {
         write_record(P, P.t0, xs);  // the initial point is always kept (resize!(..., 1))
 
         // Hairer-Norsett-Wanner initial step (OrdinaryDiffEq ode_determine_initdt), order 5
+        refresh_rate(P, P.t0);
         field(P, y, k1, (R)s);
         double d0 = 0.0, d1 = 0.0;
         double sk[D];
@@ -398,6 +413,7 @@ struct Traj {
 #pragma unroll
             for (int i = 0; i < ND; ++i) xd[i] += P.nu[(ev - 1) * ND + i];
             if constexpr (M::HAS_DELTA) M::delta(y, xd, P.parms, tj, ev);
+            refresh_rate(P, tj);
             field(P, y, k1, (R)s);  // u_modified!(integrator, true): FSAL re-evaluated
 #pragma unroll
             for (int i = 0; i < NC; ++i) xs[i] = y[i];  // caract.xc .= u
@@ -642,6 +658,7 @@ struct ModelEntry {
     pdmp_model_info info;
     int rec_words;  // RecLayout::WORDS
     int sched_jump, sched_refill;  // SchedDefaults<M>
+    int const_rate_ok;             // ConstRateOk<M>
     // launch(alg, ode, precision, records, stats, P, grid, smem, stream): returns cudaError_t
     cudaError_t (*launch)(int alg, int ode, int prec, bool records, bool stats, const KParams& P, int grid, size_t smem,
                           cudaStream_t stream);
@@ -769,6 +786,7 @@ ModelEntry make_entry(int id) {
     for (int i = 0; M::NAME[i] && i < 31; ++i) e.info.name[i] = M::NAME[i];
     e.rec_words = RecLayout<M>::WORDS;
     e.sched_jump = SchedDefaults<M>::jump; e.sched_refill = SchedDefaults<M>::refill;
+    e.const_rate_ok = ConstRateOk<M>::value;
     e.launch = &model_launch<M>;
     e.occupancy = &model_occupancy<M>;
     e.compact = &model_compact<M>;

@@ -100,6 +100,7 @@ struct SirDevT {  // examples/sir-rejection.jl:3-17 (REJ) / examples/sir.jl:6-27
     static constexpr int NC = 1, ND = 4, NR = 3, NP = 2;
     static constexpr bool HAS_BOUND = REJ, HAS_DELTA = false, ZERO_FLOW = true, HAS_CHV_FIELD = false;
     static constexpr const char* NAME = REJ ? "sir_rejection" : "sir";
+    static constexpr bool CONST_RATE_OK = true;    // rates depend on xd only
     template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) { dx[0] = R(0); }
     template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
         r[0] = R(p[0]) * (R)xd[0] * (R)xd[1];
@@ -130,6 +131,33 @@ struct StiffDev {  // test/pdmpStiff.jl:71-90
         r[1] = R(p[0]);
     }
     template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(p[0] + 100.0); }
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
+};
+
+struct StiffDeltaDev : StiffDev {  // test/pdmpStiff.jl:198-215: jumps written as a Delta! function, nu = 0
+    static constexpr bool HAS_DELTA = true;
+    static constexpr const char* NAME = "pdmp_stiff_delta";
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {
+        if (ev == 1) xd[0] += 1; else xd[1] -= 1;
+    }
+};
+
+struct RatesCstDev {  // test/testRatesCst.jl:5-24: the flow of pdmp_stiff, rates that depend on xd only
+    static constexpr int NC = 1, ND = 2, NR = 2, NP = 1;
+    static constexpr bool HAS_BOUND = false, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;
+    static constexpr bool CONST_RATE_OK = true;    // usable with ConstantRate (src/rate.jl:17-40)
+    static constexpr const char* NAME = "rates_cst";
+    template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
+        dx[0] = (xd[0] & 1) ? R(-3) * (x[0] * x[0]) : R(10) * x[0];
+    }
+    template <class R> PDMP_DEV static R rtot(const R* x, const int* xd, const double* p, R t) {
+        return (R(10) + (R)xd[0]) + R(p[0]);
+    }
+    template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
+        r[0] = R(10) + (R)xd[0];
+        r[1] = R(p[0]);
+    }
+    template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(0); }
     template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
 };
 

@@ -35,6 +35,10 @@ EXAMPLES = {
     # test/pdmpStiff.jl:92-99
     "pdmp_stiff": dict(nu=[[1, 0], [0, -1]], xc0=[1.0], xd0=[0, 0], parms=[0.0], tspan=(0.322156, 100000.0),
                        n_jumps=50),
+    # test/pdmpStiff.jl:198-215: PDMPProblem(F!, R!, Delta!, 2, xc0, xd0, parms, (ti, tf)) — reaction_number form
+    "pdmp_stiff_delta": dict(nu=2, xc0=[1.0], xd0=[0, 0], parms=[0.0], tspan=(0.322156, 100000.0), n_jumps=50),
+    # test/testRatesCst.jl:5-33: rates 10 + xd[1] and parms[1], constant between jumps
+    "rates_cst": dict(nu=[[1, 0], [0, -1]], xc0=[1.0], xd0=[0, 0], parms=[0.0], tspan=(0.0, 100000.0), n_jumps=14),
     # examples/tcp_rejection.jl:67-73
     "tcp_rejection": dict(nu=[[1, 0], [0, -1]], xc0=[0.0], xd0=[0, 0], parms=[0.0], tspan=(0.0, 100000.0),
                           n_jumps=50),
@@ -51,4 +55,6 @@ def problem(name, **override):
     """PDMPProblem of a reference example; F/R/Delta are the device functor's name."""
     e = dict(EXAMPLES[name])
     e.update(override)
+    if isinstance(e["nu"], int):   # reaction_number constructor (src/problem.jl:190-193): the jumps live in Delta
+        return PDMPProblem(name, name, name, e["nu"], e["xc0"], e["xd0"], e["parms"], e["tspan"])
     return PDMPProblem(name, name, np.array(e["nu"]), e["xc0"], e["xd0"], e["parms"], e["tspan"])

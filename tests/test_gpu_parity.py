@@ -73,6 +73,21 @@ def test_stiff_closed_form(G, golden, ode):
     assert r1.time[-1] == 4.0 and r2.time[-1] == 4.0 and r1.xc[-1, 0] == r2.xc[-1, 0]
 
 
+def test_stiff_with_delta_function(G, orc, golden):
+    # test/pdmpStiff.jl:198-215: jumps as a Delta! function with the reaction_number constructor
+    pa, pd = G.models.problem("pdmp_stiff"), G.models.problem("pdmp_stiff_delta")
+    a = G.solve(pa, G.CHVGPU("pdmp_stiff", ode="tsit5"), n_jumps=50, replay=golden["stiff_u"])
+    d = G.solve(pd, G.CHVGPU("pdmp_stiff_delta", ode="tsit5"), n_jumps=50, replay=golden["stiff_u"])
+    assert np.array_equal(a.time, d.time) and np.array_equal(a.xd, d.xd) and np.array_equal(a.xc, d.xc)
+    assert np.max(np.abs(d.time - golden["stiff_t"])) < 1e-3          # the reference's bar for this test
+    U = uniforms(5, 300, 128)
+    kw = dict(trajectories=300, n_jumps=40, replay=U, reltol=1e-10, abstol=1e-13)
+    g = G.solve(pd, G.RejectionGPU("pdmp_stiff_delta"), **{**kw, "n_jumps": 6})
+    c = orc.solve(pd, "pdmp_stiff_delta", algorithm="rejection", ode="dp5", **{**kw, "n_jumps": 6})
+    same_discrete(g, c)
+    assert relerr(g.time, c.time) < 1e-8
+
+
 @pytest.mark.parametrize("ode", ODES)
 def test_explosion_closed_form(G, golden, ode):
     pb = G.models.problem("pdmp_explosion")
@@ -483,3 +498,42 @@ def test_fp32_moments_match_fp64(G, model, tf, nj):
     # same Philox stream, FP32 vs FP64: the bulk of the trajectories follows the same discrete path
     c = G.solve(pb, G.CHVGPU(model, precision="fp32"), seed=21, reltol=1e-5, abstol=1e-7, **kw)
     assert np.mean(c.njumps == a.njumps) > 0.95
+
+
+# ---- rate wrappers (reference src/rate.jl, test/testRatesCst.jl) ---------------------------------
+
+def test_constant_rate_wrapper(G, orc):
+    from test_oracle_golden import _rates_cst_closed_form
+    U = uniforms(8, 200, 64)
+    ex = G.models.EXAMPLES["rates_cst"]
+    plain = G.models.problem("rates_cst")
+    cst = G.PDMPProblem("rates_cst", G.ConstantRate("rates_cst"), np.array(ex["nu"]), ex["xc0"], ex["xd0"], ex["parms"], ex["tspan"])
+    var = G.PDMPProblem("rates_cst", G.VariableRate("rates_cst"), np.array(ex["nu"]), ex["xc0"], ex["xd0"], ex["parms"], ex["tspan"])
+    kw = dict(trajectories=200, n_jumps=14, replay=U)
+    r0 = G.solve(plain, G.CHVGPU("rates_cst", ode="tsit5"), **kw)
+    rc = G.solve(cst, G.CHVGPU("rates_cst", ode="tsit5"), **kw)
+    rv = G.solve(var, G.CHVGPU("rates_cst", ode="tsit5"), **kw)
+    # test/testRatesCst.jl:62-72: @test rescst.time == res0.time ; @test resvar.time == res0.time
+    assert np.array_equal(rc.time, r0.time) and np.array_equal(rv.time, r0.time)
+    assert np.array_equal(rc.xd, r0.xd) and np.array_equal(rc.xc, r0.xc)
+    assert np.max(np.abs(r0[0].time - _rates_cst_closed_form(U[0], 14))) < 1e-6
+    c = orc.solve(plain, "rates_cst", algorithm="chv", ode="tsit5", **kw)
+    same_discrete(rc, c)
+    assert relerr(rc.time, c.time) < 1e-7
+    # SIR (CHV twin of examples/sir.jl): rates depend on xd only as well
+    ex = G.models.EXAMPLES["sir"]
+    sir = G.models.problem("sir")
+    sir_c = G.PDMPProblem("sir", G.ConstantRate("sir"), np.array(ex["nu"]), ex["xc0"], ex["xd0"], ex["parms"], ex["tspan"])
+    a = G.solve(sir, G.CHVGPU("sir"), trajectories=2000, n_jumps=400, seed=4)
+    b = G.solve(sir_c, G.CHVGPU("sir"), trajectories=2000, n_jumps=400, seed=4)
+    assert np.array_equal(a.xd, b.xd) and np.allclose(a.time, b.time, rtol=1e-12, atol=0)
+    assert b.counters["kernel_ms"] > 0
+    # a functor whose rates vary with xc cannot be declared constant
+    ex = G.models.EXAMPLES["tcp"]
+    bad = G.PDMPProblem("tcp", G.ConstantRate("tcp"), np.array(ex["nu"]), ex["xc0"], ex["xd0"], ex["parms"], (0.0, 10.0))
+    with pytest.raises(G.PDMPError) as ei:
+        G.solve(bad, G.CHVGPU("tcp"), trajectories=4, n_jumps=5)
+    assert ei.value.code == G._abi.ERR_UNSUPPORTED
+    with pytest.raises(NotImplementedError):
+        G.solve(G.PDMPProblem("tcp", G.CompositeRate("tcp", "tcp"), np.array(ex["nu"]), ex["xc0"], ex["xd0"], ex["parms"], (0.0, 10.0)),
+                G.CHVGPU("tcp"), trajectories=4, n_jumps=5)

@@ -63,6 +63,17 @@ def test_stiff_chv(orc, P, golden, ode):
     assert rel(r.xc[:, 0], golden["stiff_x"]) < 1e-7
 
 
+def test_stiff_with_delta_function(orc, P, golden):
+    # test/pdmpStiff.jl:198-215: PDMPProblem(F!, R!, Delta!, 2, ...) — the jumps written as a function
+    # instead of nu — gives the same trajectory as the nu form
+    pa, pd = P.models.problem("pdmp_stiff"), P.models.problem("pdmp_stiff_delta")
+    assert pd.nu.shape == (2, 2) and not pd.nu.any()
+    a = orc.solve(pa, "pdmp_stiff", algorithm="chv", ode="tsit5", n_jumps=50, replay=golden["stiff_u"])
+    d = orc.solve(pd, "pdmp_stiff_delta", algorithm="chv", ode="tsit5", n_jumps=50, replay=golden["stiff_u"])
+    assert np.array_equal(a.time, d.time) and np.array_equal(a.xd, d.xd) and np.array_equal(a.xc, d.xc)
+    assert np.max(np.abs(d.time - golden["stiff_t"])) < 1e-3
+
+
 @pytest.mark.parametrize("ode", ODES)
 def test_stiff_chv_tf_limited(orc, P, golden, ode):
     # test/pdmpStiff.jl:142-157: tspan[2] = 4.0: all jump times < tf match (2e-5), last time == tf;
@@ -184,3 +195,18 @@ def test_last_bit_quirk_flag(orc, P):
     b = orc.solve(pb, "pdmp_stiff", algorithm="chv", ode="tsit5", n_jumps=50, seed=8, ref_quirks=True)
     assert np.array_equal(a.time, b.time) and np.array_equal(a.xc[:-1], b.xc[:-1])
     assert abs(a.xc[-1, 0] - b.xc[-1, 0]) < 1e-2 * max(1.0, abs(a.xc[-1, 0]))
+
+
+def _rates_cst_closed_form(U, nj):
+    # test/testRatesCst.jl: total rate 10 + xd[1] (+ parms[1] = 0) is constant between jumps, so the CHV
+    # time change is linear: t_k = sum_j E_j / (10 + j); draws: U0 -> E0, then (U_event, U_E) per jump
+    E = -np.log(np.concatenate([[U[0]], U[2::2]]))[:nj - 1]
+    return np.concatenate([[0.0], np.cumsum(E / (10.0 + np.arange(nj - 1)))])
+
+
+def test_rates_cst_closed_form(orc, P):
+    U = np.clip(np.random.default_rng(8).random(64), 2.0 ** -53, 1 - 2.0 ** -53)
+    pb = P.models.problem("rates_cst")
+    r = orc.solve(pb, "rates_cst", algorithm="chv", ode="tsit5", n_jumps=14, replay=U, reltol=1e-10, abstol=1e-12)
+    assert np.max(np.abs(r.time - _rates_cst_closed_form(U, 14))) < 1e-10
+    assert np.array_equal(r.xd[:, 0], np.arange(14)) and np.all(r.xd[:, 1] == 0)
