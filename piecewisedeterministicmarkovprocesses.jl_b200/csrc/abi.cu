@@ -258,11 +258,19 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     P.n_traj = n; P.traj_id_offset = d->traj_id_offset;
     P.xc0_per_traj = d->xc0_per_traj; P.xd0_per_traj = d->xd0_per_traj;
     for (int i = 0; i < MAXP; ++i) P.parms[i] = i < d->n_parms ? d->parms[i] : 0.0;
+    // the kernels hold xd and nu as int32 (widened to the reference's Int64 on output)
     for (int r = 0; r < NR; ++r)
         for (int c = 0; c < ND; ++c) {
             const long long v = d->nu_col_major ? d->nu[(size_t)c * NR + r] : d->nu[(size_t)r * ND + c];
+            if (v > 0x3fffffffLL || v < -0x3fffffffLL) return fail(PDMP_ERR_INVALID, "nu entries must fit in 31 bits");
             P.nu[r * ND + c] = (int)v;
         }
+    {
+        const size_t nchk = (size_t)(d->xd0_per_traj ? d->n_traj : 1) * ND;
+        for (size_t i = 0; i < nchk; ++i)
+            if (d->xd0[i] > 0x3fffffffLL || d->xd0[i] < -0x3fffffffLL)
+                return fail(PDMP_ERR_INVALID, "xd0 entries must fit in 31 bits");
+    }
     P.t0 = d->t0; P.tf = d->tf;
     P.rate_const = d->rate_kind == 1;
     P.reltol = o->reltol; P.abstol = o->abstol;
@@ -421,6 +429,8 @@ static int upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc0_per_traj,
     }
     if (xd0) {
         const size_t cnt = (size_t)(xd0_per_traj ? e->n : 1) * ND;
+        for (size_t i = 0; i < cnt; ++i)
+            if (xd0[i] > 0x3fffffffLL || xd0[i] < -0x3fffffffLL) return fail(PDMP_ERR_INVALID, "xd0 entries must fit in 31 bits");
         if (cnt > e->cap_xd0) {
             CK(cudaStreamSynchronize(st));
             CK(cudaFree(e->d_xd0)); e->d_xd0 = nullptr; e->cap_xd0 = 0;
