@@ -537,3 +537,43 @@ def test_constant_rate_wrapper(G, orc):
     with pytest.raises(NotImplementedError):
         G.solve(G.PDMPProblem("tcp", G.CompositeRate("tcp", "tcp"), np.array(ex["nu"]), ex["xc0"], ex["xd0"], ex["parms"], (0.0, 10.0)),
                 G.CHVGPU("tcp"), trajectories=4, n_jumps=5)
+
+
+# ---- BASELINE.json's full size (C2: 10^7 TCP trajectories, tf = 200, n_jumps = 1000) -----------------
+
+@pytest.mark.timeout(600)
+def test_c2_full_size_properties(G):
+    """Size-independent properties at the benchmark's own size.  The 1.3e9 saved points stay in HBM
+    (26 GB would have to cross PCIe and be walked by numpy); what is checked is everything the
+    per-trajectory arrays, the counters and the on-GPU statistics pin down."""
+    n = 10_000_000
+    pb = G.models.problem("tcp", tspan=(0.0, 200.0))
+    xc0 = 0.5 + np.random.default_rng(2024).random((n, 1))
+    st = [50.0, 100.0, 150.0, 200.0]
+    ens = G.Ensemble(pb, G.CHVGPU("tcp"), trajectories=n, n_jumps=1000, sample_times=st, max_records=n * 160,
+                     xc0=xc0, tstop_policy=1, xd_transport="auto")
+    ens.run(seed=7)
+    r = ens.fetch(records=False, copy=True)     # (views into the ensemble's pinned staging die with the next run / close)
+    c = ens.counters()
+    ok, cap, stall = (r.status == G._abi.ST_OK), (r.status == G._abi.ST_HIT_NJUMPS), (r.status == G._abi.ST_NO_PROGRESS)
+    assert ok.sum() + cap.sum() + stall.sum() == n                      # no other status at this size
+    assert ok.mean() > 0.85 and 0.005 < cap.mean() < 0.05
+    assert np.all(r.njumps[cap] == 1000) and np.all(r.njumps <= 1000) and np.all(r.njumps >= 2)
+    assert c["total_candidates"] == int((r.njumps - 1).sum())           # every threshold is counted once
+    # saved points: the initial point + one per threshold; the stalled threshold of a NO_PROGRESS path is not saved
+    assert c["total_records"] == int(r.njumps.sum()) - int(stall.sum())
+    assert c["total_jumps"] == c["total_candidates"] - int(ok.sum())    # the overshooting threshold of an OK path fires no jump
+    # statistics: every trajectory alive at a sample time is counted there exactly once
+    assert np.all(np.diff(r.stat_count[:, 0]) <= 0) and r.stat_count[0, 0] <= n
+    assert r.stat_count[-1, 0] == ok.sum()                              # reached tf  <=>  status OK
+    assert np.all(r.stat_sum[:, 2] == r.stat_count[:, 2])               # xd[2] is 1 for ever (examples/tcp.jl)
+    # determinism, and independence of the schedule: same seed, sharded in two resident runs
+    ens.run(seed=7)
+    r2 = ens.fetch(records=False)
+    assert np.array_equal(r2.njumps, r.njumps) and np.array_equal(r2.status, r.status)
+    assert np.allclose(r2.stat_sum, r.stat_sum, rtol=1e-12)             # FP64 atomics: order-dependent round-off only
+    ens.close()
+    h = n // 2
+    a = G.solve(pb, G.CHVGPU("tcp"), trajectories=h, traj_id_offset=h, n_jumps=1000, seed=7, xc0=xc0[h:], no_records=True,
+                tstop_policy=1)
+    assert np.array_equal(a.njumps, r.njumps[h:]) and np.array_equal(a.status, r.status[h:])
