@@ -120,7 +120,7 @@ struct pdmp_ensemble {
     unsigned long long n = 0, chunk_n = 0;  // chunk_n: trajectories per chunk of a HOST-mode run
     int n_chunks = 0;
     bool shared_pool = false;  // one full-size pool for the whole ensemble (then resident runs are ONE kernel)
-    int cur_chunks = 1; unsigned long long cur_chunk_n = 0;  // chunking of the last run
+    int cur_chunks = 1; std::vector<unsigned long long> cur_bounds;  // chunking of the last run: [bounds[k], bounds[k+1])
     KParams P{};
     bool records = false, stats = false;
     int grid = 0;
@@ -455,7 +455,7 @@ int32_t pdmp_ensemble_upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc
 
 // D2H of chunk k's slice of every per-trajectory and per-record array (host mode)
 static int queue_chunk_d2h(pdmp_ensemble* e, int k, bool fetch_records) {
-    const unsigned long long a = (unsigned long long)k * e->cur_chunk_n, b = std::min(e->n, a + e->cur_chunk_n);
+    const unsigned long long a = e->cur_bounds[k], b = e->cur_bounds[k + 1];
     const int NC = e->m->info.n_c, ND = e->m->info.n_d;
     CK(cudaEventSynchronize(e->ev_done[k]));  // chunk compacted; its record range is now known on the host
     cudaStream_t st = e->copy;
@@ -503,12 +503,17 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
     // pools are per-stream) are chunked so that compaction / D2H of chunk k overlap chunk k+1
     // (measured: chunking a resident run costs 5 % at 4 chunks and 19 % at 10 — every chunk has its own tail)
     const int nch = (!host_mode && e->shared_pool) ? 1 : e->n_chunks;
-    const unsigned long long chn = nch == 1 ? std::max<unsigned long long>(e->n, 1) : e->chunk_n;
-    e->cur_chunks = nch; e->cur_chunk_n = chn;
+    std::vector<unsigned long long>& bounds = e->cur_bounds;
+    bounds.assign(1, 0ull);
+    // (also measured: an unequal 2-way split so that the compaction of the first part overlaps the second
+    //  kernel gains nothing — one co-resident compaction CTA per SM moves only ~0.6 TB/s)
+    if (nch == 1) bounds.push_back(e->n);
+    else for (int k = 1; k <= nch; ++k) bounds.push_back(std::min(e->n, (unsigned long long)k * e->chunk_n));
+    e->cur_chunks = nch;
     for (int k = 0; k < nch && e->n; ++k) {
         const int q = k % NS;
         cudaStream_t st = e->cs[q];
-        const unsigned long long a = (unsigned long long)k * chn, b = std::min(e->n, a + chn);
+        const unsigned long long a = bounds[k], b = bounds[k + 1];
         KParams Pk = e->P;
         Pk.n_traj = b - a;
         Pk.traj_id_offset = e->P.traj_id_offset + a;
