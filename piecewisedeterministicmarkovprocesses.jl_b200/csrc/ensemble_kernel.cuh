@@ -707,11 +707,26 @@ __global__ void __launch_bounds__(128, 16) compact_kernel(const KParams P, const
             __stcs(time + o, w[0]);
 #pragma unroll
             for (int c = 0; c < NC; ++c) __stcs(xc + o * NC + c, w[1 + c]);
+            if constexpr (sizeof(XT) == 2 && ND % 2 == 0) {
+                // int16 transport: a pair of components is one 32-bit store
+                unsigned* dst = reinterpret_cast<unsigned*>(xd + o * ND);
 #pragma unroll
-            for (int c = 0; c < ND; ++c) {
-                const double pw = w[1 + NC + c / 2];
-                const int v = (c & 1) ? __double2hiint(pw) : __double2loint(pw);
-                xd[o * ND + c] = (XT)v;
+                for (int c = 0; c < ND; c += 2) {
+                    const double pw = w[1 + NC + c / 2];
+                    __stcs(dst + c / 2, ((unsigned)__double2loint(pw) & 0xffffu) | ((unsigned)__double2hiint(pw) << 16));
+                }
+            } else if constexpr (sizeof(XT) == 4 && ND % 2 == 0) {
+                // int32 transport: the packed pool word is already the CSR layout
+                double* dst = reinterpret_cast<double*>(xd + o * ND);
+#pragma unroll
+                for (int c = 0; c < ND; c += 2) __stcs(dst + c / 2, w[1 + NC + c / 2]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < ND; ++c) {
+                    const double pw = w[1 + NC + c / 2];
+                    const int v = (c & 1) ? __double2hiint(pw) : __double2loint(pw);
+                    xd[o * ND + c] = (XT)v;
+                }
             }
         }
     }
