@@ -319,9 +319,10 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ics_e.nbytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps, "trajectories_per_gpu": n_e2e,
                     "ms_per_step": 1e3 * float(e.item()) / e2e_steps},
-            "gpu_launches": 3 * n_chunks * args.steps,
-            "gpu_launches_note": f"per step: {n_chunks} chunks x (ensemble_kernel + chunk_close_kernel + compact_kernel), ours; "
-                                 "plus cub::DeviceScan per chunk and memsets",
+            "gpu_launches": 3 * args.steps,
+            "gpu_launches_note": "timed (resident) region, per step: ensemble_kernel + chunk_close_kernel + compact_kernel, ours; "
+                                 "plus cub::DeviceScan and memsets.  The e2e region launches the same three per chunk "
+                                 f"({n_chunks} chunks per step)",
             "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
                          "traffic": NCU_DRAM_BYTES_PER_RECORD["ensemble_kernel"] * records / args.steps,
                          "traffic_note": "bytes per launch = ncu-measured DRAM bytes per saved record (profiles/) x records of one "

@@ -374,8 +374,9 @@ struct Integrator {
             double q11 = 0, q;
             if (EEst == 0.0) q = 1.0 / QMAX;
             else {
-                q11 = std::pow(EEst, BETA1);
-                q = q11 / std::pow(qold, BETA2);
+                // OrdinaryDiffEq evaluates these powers with its Float32 `fastpower`; single-precision powf here
+                q11 = (double)powf((float)EEst, (float)BETA1);
+                q = q11 / (double)powf((float)qold, (float)BETA2);
                 q = std::max(1.0 / QMAX, std::min(1.0 / QMIN, q / GAMMA));
             }
             if (EEst <= 1.0) {

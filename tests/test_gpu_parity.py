@@ -577,3 +577,14 @@ def test_c2_full_size_properties(G):
     a = G.solve(pb, G.CHVGPU("tcp"), trajectories=h, traj_id_offset=h, n_jumps=1000, seed=7, xc0=xc0[h:], no_records=True,
                 tstop_policy=1)
     assert np.array_equal(a.njumps, r.njumps[h:]) and np.array_equal(a.status, r.status[h:])
+
+
+def test_rejection_counts_do_not_depend_on_the_ode_pair(G):
+    # test/runtests.jl:46-49 (examples/tcp_rejection.jl:137-142): njumps and nrejected are equal across solvers
+    U = uniforms(21, 400, 400)
+    for model, nj in (("tcp_rejection", 50), ("pdmp_stiff", 6), ("neuron_eva", 60)):
+        pb = G.models.problem(model)
+        a = G.solve(pb, G.RejectionGPU(model, ode="dp5"), trajectories=400, n_jumps=nj, replay=U)
+        b = G.solve(pb, G.RejectionGPU(model, ode="tsit5"), trajectories=400, n_jumps=nj, replay=U)
+        assert np.array_equal(a.njumps, b.njumps) and np.array_equal(a.nrejected, b.nrejected), model
+        assert np.array_equal(a.xd, b.xd) and np.allclose(a.time, b.time, rtol=1e-5, atol=1e-7), model
