@@ -29,13 +29,16 @@
 extern "C" {
 #endif
 
-#define PDMP_ABI_VERSION 6
+#define PDMP_ABI_VERSION 7
 
 /* ---- enumerations ------------------------------------------------------------------ */
 
 /* algorithm: reference `CHV(ode)` (src/chvdiffeq.jl:2-4) / `Rejection(ode)`
  * (src/rejectiondiffeq.jl:1-3) */
-enum { PDMP_ALG_CHV = 0, PDMP_ALG_REJECTION = 1 };
+/* REJECTION_EXACT: thinning with a user-supplied EXACT flow instead of an ODE solve, reference
+ * `RejectionExact()` (src/rejection.jl:1, :3-91, :113-116); for models registered with
+ * exact_flow = 1 (many continuous variables: one WARP per trajectory, not one thread). */
+enum { PDMP_ALG_CHV = 0, PDMP_ALG_REJECTION = 1, PDMP_ALG_REJECTION_EXACT = 2 };
 
 /* explicit adaptive 5(4) pair used for the flow; TSIT5 is the reference's `Tsit5()`,
  * DP5 the Dormand-Prince pair named by the north star. Same controller for both. */
@@ -90,6 +93,8 @@ typedef struct pdmp_model_info {
     int32_t has_bound;  /* R returns (total, bound): usable with PDMP_ALG_REJECTION        */
     int32_t has_delta;  /* model has a Delta(xc, xd, p, t, ev) acting after nu            */
     int32_t zero_flow;  /* F == F_dummy (reference src/problem.jl:4-7)                    */
+    int32_t exact_flow; /* the functor is an exact flow Phi: PDMP_ALG_REJECTION_EXACT only   */
+    int32_t reserved0;
     char name[32];
 } pdmp_model_info;
 
@@ -164,6 +169,10 @@ typedef struct pdmp_solve_opts {
                                         the host bindings check this bound before asking.
                                      Narrow transport cuts the device->host bytes per saved
                                      point; the bindings widen per trajectory on access.    */
+    int32_t save_c_count;         /* REJECTION_EXACT: save only the first save_c_count
+                                     continuous / save_d_count discrete components of every  */
+    int32_t save_d_count;         /* point (0: all — the reference saves all of them,
+                                     src/rejection.jl:32); result.n_c / n_d report the counts */
 } pdmp_solve_opts;
 
 /* ---- result ------------------------------------------------------------------------ */

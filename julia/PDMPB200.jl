@@ -20,9 +20,9 @@ import PiecewiseDeterministicMarkovProcesses as PDMP
 import SciMLBase
 using Libdl
 
-export CHVGPU, RejectionGPU, EnsembleResult, device_count, list_models
+export CHVGPU, RejectionGPU, RejectionExactGPU, EnsembleResult, device_count, list_models
 
-const ABI_VERSION = 6
+const ABI_VERSION = 7
 const libpdmp = Ref{String}(get(ENV, "PDMP_B200_LIB", "libpdmp_b200.so"))
 
 # ---- algorithm types ---------------------------------------------------------------------
@@ -53,8 +53,23 @@ struct RejectionGPU <: PDMP.AbstractRejection
     RejectionGPU(model; ode = :dp5, precision = :fp64) = new(Symbol(model), ode, precision)
 end
 
+"""
+    RejectionExactGPU(model)
+
+Ensemble thinning with the model's EXACT flow (no ODE solve); replaces `RejectionExact()`
+(reference src/rejection.jl:1, :3-91).  One warp per trajectory: for models with many continuous
+variables (examples/neuron_rejection_exact.jl, N = 100).
+"""
+struct RejectionExactGPU <: PDMP.AbstractRejectionExact
+    model::Symbol
+    ode::Symbol
+    precision::Symbol
+    RejectionExactGPU(model) = new(Symbol(model), :dp5, :fp64)
+end
+
 algorithm_code(::CHVGPU) = Int32(0)        # PDMP_ALG_CHV
 algorithm_code(::RejectionGPU) = Int32(1)  # PDMP_ALG_REJECTION
+algorithm_code(::RejectionExactGPU) = Int32(2)  # PDMP_ALG_REJECTION_EXACT
 ode_code(a) = a.ode === :tsit5 ? Int32(1) : a.ode === :dp5 ? Int32(0) : error("ode must be :dp5 or :tsit5")
 precision_code(a) = a.precision === :fp32 ? Int32(1) : a.precision === :fp64 ? Int32(0) : error("precision must be :fp64 or :fp32")
 
@@ -68,6 +83,8 @@ struct ModelInfo
     has_bound::Int32
     has_delta::Int32
     zero_flow::Int32
+    exact_flow::Int32
+    reserved0::Int32
     name::NTuple{32, UInt8}
 end
 
@@ -115,6 +132,8 @@ struct SolveOpts
     tstop_policy::Int32
     ref_quirks::Int32
     xd_bytes::Int32
+    save_c_count::Int32
+    save_d_count::Int32
 end
 
 mutable struct CResult
@@ -235,12 +254,13 @@ reference's order), `sample_times`, `hist = [(component, lo, hi), ...]`, `hist_b
 Per-trajectory failures (the reference's `@assert`s, src/chvdiffeq.jl:145,
 src/rejectiondiffeq.jl:33) are returned in `status`, never thrown.
 """
-function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, RejectionGPU};
+function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, RejectionGPU, RejectionExactGPU};
                          trajectories::Integer = 1, n_jumps = nothing, save_positions = (false, true),
                          reltol = 1e-7, abstol = 1e-9, seed::Integer = 0, replay = nothing,
                          sample_times = Float64[], hist = Tuple{Int, Float64, Float64}[], hist_bins = 0,
                          device = 0, traj_id_offset = 0, xc0 = nothing, xd0 = nothing, max_records = 0,
                          no_records = false, max_attempts = 0, tstop_policy = 0, xd_bytes = 8,
+                         save_c_count = 0, save_d_count = 0,
                          verbose = false, save_rate = false, finalizer = nothing, kwargs...)
     (n_jumps === nothing || !isfinite(n_jumps)) &&
         error("n_jumps must be given and finite for an ensemble solve")
@@ -250,6 +270,8 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
     nu = Matrix{Int64}(car.pdmpjump.nu)                        # column-major: nu_col_major = 1
     (size(nu, 1) == info.n_r && size(nu, 2) == info.n_d && length(car.xc0) == info.n_c) ||
         error("problem shape does not match device model $(algo.model)")
+    (algo isa RejectionExactGPU) == (info.exact_flow != 0) ||
+        error("RejectionExactGPU needs an exact-flow device model (and only it can run one)")
     xc = xc0 === nothing ? Vector{Float64}(car.xc0) : Matrix{Float64}(xc0)
     xd = xd0 === nothing ? Vector{Int64}(car.xd0) : Matrix{Int64}(xd0)
     parms = car.parms isa AbstractVector ? Vector{Float64}(car.parms) : Float64[]
@@ -270,7 +292,7 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
                       isempty(hlo) ? C_NULL : pointer(hlo), isempty(hhi) ? C_NULL : pointer(hhi), maxrec,
                       algorithm_code(algo), ode_code(algo), precision_code(algo), isempty(ru) ? 0 : 1,
                       save_positions[1], save_positions[2], no_records, length(st), length(hc),
-                      isempty(hc) ? 0 : hist_bins, device, tstop_policy, 0, xd_bytes)
+                      isempty(hc) ? 0 : hist_bins, device, tstop_policy, 0, xd_bytes, save_c_count, save_d_count)
         end
         rc = ccall((:pdmp_solve_ensemble, libpdmp[]), Int32, (Ref{ProblemDesc}, Ref{SolveOpts}, Ref{CResult}),
                    desc, opts(max_records), res)

@@ -925,6 +925,106 @@ int dispatch_model(int id, Fn&& fn) {
     }
 }
 
+// ------------------------------------------------------------------------------------
+// RejectionExact, reference src/rejection.jl:3-91 (solve(problem, Flow)) and :113-116, for the
+// exact-flow model of examples/neuron_rejection_exact.jl (N = 100 neurons).  Sequential sums, as
+// the Julia loops write them.  Model id = N_MODELS (after the ODE models).
+// ------------------------------------------------------------------------------------
+struct NeuronMfModel {
+    static constexpr int N = 100, NP = 1;
+    static constexpr const char* NAME = "neuron_mf";
+    static double f(double x) { const double x2 = x * x, x4 = x2 * x2; return x4 * x4; }          // x^8, :8-10
+    static void Phi(double* x, const int64_t*, const double*, double t0, double t1) {              // :12-20
+        double sum = 0;
+        for (int i = 0; i < N; ++i) sum += x[i];
+        const double xbar = sum / N, e = std::exp(-0.24 * (t1 - t0));
+        for (int i = 0; i < N; ++i) x[i] = xbar + e * (x[i] - xbar);
+    }
+    static void R(double* rate, const double* x, const int64_t*, const double*, double, bool issum, double* out) {   // :22-36
+        out[1] = N * f(1.201);
+        if (!issum) { for (int i = 0; i < N; ++i) rate[i] = f(x[i]); out[0] = -1.0; }
+        else { double res = 0; for (int i = 0; i < N; ++i) res += f(x[i]); out[0] = res; }
+    }
+    static void Delta(double* x, int64_t* xd, const double*, double, int ev) {                     // :38-47
+        for (int i = 0; i < N; ++i) x[i] += 0.98 / N;
+        x[ev - 1] = 0.0;
+        xd[ev - 1] += 1;
+    }
+};
+
+template <class M>
+int run_exact(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_result* res) {
+    constexpr int N = M::N;
+    if (o->algorithm != PDMP_ALG_REJECTION_EXACT) { g_err = "exact-flow model: use RejectionExact"; return PDMP_ERR_MODEL; }
+    if (o->n_sample_times) { g_err = "sample_times are not available with RejectionExact"; return PDMP_ERR_UNSUPPORTED; }
+    const uint64_t n = d->n_traj;
+    const int kc = o->save_c_count > 0 ? std::min(o->save_c_count, N) : N;
+    const int kd = o->save_d_count > 0 ? std::min(o->save_d_count, N) : N;
+    auto* own = new ResultOwner();
+    own->offsets.assign(n + 1, 0); own->njumps.assign(n, 0); own->nrejected.assign(n, 0); own->status.assign(n, 0);
+    uint64_t jumps = 0, cands = 0;
+    for (uint64_t g = 0; g < n; ++g) {
+        double x[N], rate[N], ppf[2];
+        int64_t xd[N];
+        for (int i = 0; i < N; ++i) {
+            x[i] = d->xc0[(d->xc0_per_traj ? g * N : 0) + i];
+            xd[i] = d->xd0[(d->xd0_per_traj ? g * N : 0) + i];
+        }
+        DrawStream rng;
+        rng.mode = o->rng_mode; rng.replay = o->replay_u ? o->replay_u + g * o->replay_stride : nullptr;
+        rng.replay_len = o->replay_stride; rng.gid = d->traj_id_offset + g; rng.seed = o->seed;
+        double t = d->t0;
+        double dte = -std::log(rng.next());                                     // init!, src/problem.jl:153
+        int64_t nsteps = 1, nrej = 0;
+        int status = PDMP_ST_OK;
+        auto save = [&]() {
+            own->time.push_back(t);
+            for (int i = 0; i < kc; ++i) own->xc.push_back(x[i]);
+            for (int i = 0; i < kd; ++i) own->xd.push_back(xd[i]);
+        };
+        save();
+        M::R(rate, x, xd, d->parms, t, true, ppf);                              // :45
+        while (t < d->tf && nsteps < o->n_jumps && status == PDMP_ST_OK) {     // :49
+            bool reject = true;
+            while (reject && nsteps < o->n_jumps) {                            // :52
+                const double t1 = std::min(d->tf, t + dte / ppf[1]);           // :53
+                M::Phi(x, xd, d->parms, t, t1);                                // :54-58
+                t = t1;
+                M::R(rate, x, xd, d->parms, t, true, ppf);                     // :62
+                ++cands;
+                if (!(ppf[0] <= ppf[1])) { status = PDMP_ST_BOUND_VIOLATED; break; }   // @assert :63
+                if (t == d->tf) reject = false;
+                else reject = rng.next() < 1 - ppf[0] / ppf[1];                // :67
+                dte = -std::log(rng.next());                                   // :69
+                if (reject) ++nrej;
+                if (rng.exhausted) { status = PDMP_ST_REPLAY_EXHAUSTED; break; }
+            }
+            if (status != PDMP_ST_OK) break;
+            M::R(rate, x, xd, d->parms, t, false, ppf);                        // :76
+            if (t < d->tf) {                                                    // :78
+                const int ev = pfsample(rate, N, rng.next());                   // :81
+                M::Delta(x, xd, d->parms, t, ev);                               // :83 (nu is all zero)
+                ++jumps;
+                if (rng.exhausted) { status = PDMP_ST_REPLAY_EXHAUSTED; break; }
+            }
+            ++nsteps;                                                           // :86
+            save();                                                             // :87-89
+        }
+        if (status == PDMP_ST_OK && t < d->tf) status = PDMP_ST_HIT_NJUMPS;
+        own->njumps[g] = nsteps; own->nrejected[g] = nrej; own->status[g] = (uint8_t)status;
+        own->offsets[g + 1] = own->time.size();
+    }
+    std::memset(res, 0, sizeof(*res));
+    res->n_traj = n; res->total_records = own->time.size(); res->records_needed = res->total_records;
+    res->offsets = own->offsets.data(); res->time = own->time.data(); res->xc = own->xc.data();
+    res->xd = own->xd.data(); res->njumps = own->njumps.data(); res->nrejected = own->nrejected.data();
+    res->status = own->status.data();
+    res->total_jumps = jumps; res->total_candidates = cands;
+    res->n_c = kc; res->n_d = kd; res->xd_bytes = 8; res->n_comp = kc + kd;
+    res->owner = own;
+    return PDMP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -935,8 +1035,15 @@ int32_t pdmp_oracle_max_threads(void) {
     const int n = (int)std::thread::hardware_concurrency();
     return n > 0 ? n : 1;
 }
-int32_t pdmp_oracle_model_count(void) { return N_MODELS; }
+int32_t pdmp_oracle_model_count(void) { return N_MODELS + 1; }
 int32_t pdmp_oracle_model_info_by_id(int32_t id, pdmp_model_info* out) {
+    if (id == N_MODELS && out) {   // the exact-flow model
+        std::memset(out, 0, sizeof(*out));
+        out->id = id; out->n_c = out->n_d = out->n_r = NeuronMfModel::N; out->n_parms = NeuronMfModel::NP;
+        out->has_bound = 1; out->has_delta = 1; out->exact_flow = 1;
+        std::strncpy(out->name, NeuronMfModel::NAME, 31);
+        return PDMP_OK;
+    }
     return dispatch_model(id, [&](auto* m) {
         using M = std::remove_pointer_t<decltype(m)>;
         fill_info<M>(id, out);
@@ -949,6 +1056,8 @@ int32_t pdmp_oracle_solve_ensemble(const pdmp_problem_desc* d, const pdmp_solve_
     if (!d || !o || !res) { g_err = "null argument"; return PDMP_ERR_INVALID; }
     if (o->n_jumps < 1) { g_err = "n_jumps must be >= 1"; return PDMP_ERR_INVALID; }
     if (o->rng_mode == PDMP_RNG_REPLAY && !o->replay_u) { g_err = "replay_u is null"; return PDMP_ERR_INVALID; }
+    if (d->model_id == N_MODELS) return run_exact<NeuronMfModel>(d, o, res);
+    if (o->algorithm == PDMP_ALG_REJECTION_EXACT) { g_err = "model has no exact flow"; return PDMP_ERR_MODEL; }
     return dispatch_model(d->model_id, [&](auto* m) {
         using M = std::remove_pointer_t<decltype(m)>;
         return run_ensemble<M>(d, o, res);

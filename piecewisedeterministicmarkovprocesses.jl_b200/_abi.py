@@ -1,13 +1,13 @@
-"""ctypes mirror of include/pdmp_b200.h (ABI version 6).
+"""ctypes mirror of include/pdmp_b200.h (ABI version 7).
 
 Pure declarations: no library is loaded here, so the oracle loader (oracle/oracle.py, test
 infrastructure) can share the struct layouts without touching the product library.
 """
 import ctypes as C
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
-ALG_CHV, ALG_REJECTION = 0, 1
+ALG_CHV, ALG_REJECTION, ALG_REJECTION_EXACT = 0, 1, 2
 ODE_DP5, ODE_TSIT5 = 0, 1
 RNG_PHILOX, RNG_REPLAY = 0, 1
 PREC_FP64, PREC_FP32 = 0, 1
@@ -29,7 +29,8 @@ c_uint8_p = C.POINTER(C.c_uint8)
 class ModelInfo(C.Structure):
     _fields_ = [("id", C.c_int32), ("n_c", C.c_int32), ("n_d", C.c_int32), ("n_r", C.c_int32),
                 ("n_parms", C.c_int32), ("has_bound", C.c_int32), ("has_delta", C.c_int32),
-                ("zero_flow", C.c_int32), ("name", C.c_char * 32)]
+                ("zero_flow", C.c_int32), ("exact_flow", C.c_int32), ("reserved0", C.c_int32),
+                ("name", C.c_char * 32)]
 
 
 class ProblemDesc(C.Structure):
@@ -50,7 +51,8 @@ class SolveOpts(C.Structure):
                 ("rng_mode", C.c_int32), ("save_pre", C.c_int32), ("save_post", C.c_int32),
                 ("no_records", C.c_int32), ("n_sample_times", C.c_int32), ("hist_n", C.c_int32),
                 ("hist_bins", C.c_int32), ("device", C.c_int32), ("tstop_policy", C.c_int32),
-                ("ref_quirks", C.c_int32), ("xd_bytes", C.c_int32)]
+                ("ref_quirks", C.c_int32), ("xd_bytes", C.c_int32),
+                ("save_c_count", C.c_int32), ("save_d_count", C.c_int32)]
 
 
 class Result(C.Structure):

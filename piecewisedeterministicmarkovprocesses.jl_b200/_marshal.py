@@ -10,7 +10,7 @@ from .problem import EnsembleResult
 
 _ODE = {"dp5": _abi.ODE_DP5, "tsit5": _abi.ODE_TSIT5, _abi.ODE_DP5: _abi.ODE_DP5,
         _abi.ODE_TSIT5: _abi.ODE_TSIT5}
-_ALG = {"chv": _abi.ALG_CHV, "rejection": _abi.ALG_REJECTION}
+_ALG = {"chv": _abi.ALG_CHV, "rejection": _abi.ALG_REJECTION, "rejection_exact": _abi.ALG_REJECTION_EXACT}
 
 
 def _ptr(a, ctype):
@@ -21,7 +21,7 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
           n_jumps=None, save_positions=(False, True), reltol=1e-7, abstol=1e-9, seed=0,
           replay=None, sample_times=None, hist=None, hist_bins=0, precision="fp64",
           device=0, max_attempts=0, max_records=0, no_records=False, tstop_policy=0,
-          ref_quirks=False, xc0=None, xd0=None, xd_transport="int64"):
+          ref_quirks=False, xc0=None, xd0=None, xd_transport="int64", save_c_count=0, save_d_count=0):
     """Returns (desc, opts, keepalive).  `info` is the model's pdmp_model_info.
 
     xc0 / xd0 override the problem's (broadcast) initial conditions with per-trajectory
@@ -114,6 +114,7 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
     if xd_transport == "int16" and (bound >= 32768 or info.has_delta):
         raise ValueError("xd_transport='int16' is not provably exact for this problem (bound %d)" % bound)
     o.xd_bytes = {"int64": 8, "int32": 4, "int16": 2}[xd_transport]
+    o.save_c_count, o.save_d_count = int(save_c_count), int(save_d_count)
     return d, o, keep
 
 

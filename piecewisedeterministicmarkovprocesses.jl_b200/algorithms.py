@@ -3,6 +3,7 @@
 
     AbstractPDMPAlgorithm <- AbstractCHV       <- CHVGPU
                           <- AbstractRejection <- RejectionGPU
+                                               <- AbstractRejectionExact <- RejectionExactGPU
 
 `CHVGPU(model, ode="dp5")` replaces `CHV(Tsit5())` (src/chvdiffeq.jl:2-4), and
 `RejectionGPU(model, ode="dp5")` replaces `Rejection(Tsit5())` (src/rejectiondiffeq.jl:1-3),
@@ -23,6 +24,10 @@ class AbstractRejection(AbstractPDMPAlgorithm):
     pass
 
 
+class AbstractRejectionExact(AbstractRejection):
+    pass
+
+
 class _GPUAlg:
     def __init__(self, model, ode="dp5", precision="fp64"):
         if ode not in ("dp5", "tsit5"):
@@ -39,3 +44,12 @@ class CHVGPU(_GPUAlg, AbstractCHV):
 
 class RejectionGPU(_GPUAlg, AbstractRejection):
     algorithm = "rejection"
+
+
+class RejectionExactGPU(_GPUAlg, AbstractRejectionExact):
+    """`RejectionExactGPU(model)` replaces `RejectionExact()` (reference src/rejection.jl:1, :3-91): thinning
+    with the model's EXACT flow instead of an ODE solve, one warp per trajectory (csrc/exact_kernel.cuh)."""
+    algorithm = "rejection_exact"
+
+    def __init__(self, model):
+        super().__init__(model, ode="dp5", precision="fp64")

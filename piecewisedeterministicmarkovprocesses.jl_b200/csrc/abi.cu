@@ -17,6 +17,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "ensemble_kernel.cuh"
+#include "exact_kernel.cuh"
 
 namespace pdmp {
 // one translation unit per model (parallel nvcc), collected here
@@ -31,6 +32,21 @@ static const std::vector<ModelEntry>& registry() {
         entry_tcp_rejection(6), entry_pdmp_explosion(7), entry_neuron_eva(8),
         entry_pdmp_stiff_delta(9), entry_rates_cst(10)};
     return r;
+}
+
+// exact-flow models (PDMP_ALG_REJECTION_EXACT, one warp per trajectory); ids follow the registry above
+static const std::vector<ExactEntry>& exact_registry() {
+    static const std::vector<ExactEntry> r = {make_exact_entry<NeuronMfDev>()};
+    return r;
+}
+static pdmp_model_info exact_info(int k) {
+    const ExactEntry& x = exact_registry()[k];
+    pdmp_model_info i{};
+    i.id = (int)registry().size() + k;
+    i.n_c = i.n_d = i.n_r = x.n; i.n_parms = x.n_parms;
+    i.has_bound = 1; i.has_delta = 1; i.zero_flow = 0; i.exact_flow = 1;
+    for (int c = 0; x.name[c] && c < 31; ++c) i.name[c] = x.name[c];
+    return i;
 }
 
 static thread_local std::string g_err;
@@ -134,6 +150,7 @@ struct pdmp_ensemble {
     unsigned int* d_segtab = nullptr;
     unsigned long long* d_nrec = nullptr;
     long long* d_njumps = nullptr; long long* d_nrej = nullptr; unsigned char* d_status = nullptr;
+    double* d_st_time = nullptr; double* d_st_xc = nullptr; long long* d_st_xd = nullptr;  // exact-flow path: strided records
     unsigned long long* d_offsets = nullptr; double* d_time = nullptr; double* d_xc = nullptr; unsigned char* d_xd = nullptr;
     int xb = 8;  // bytes per saved discrete component (opts.xd_bytes)
     void* d_scan[NS] = {}; size_t scan_bytes = 0;
@@ -159,7 +176,7 @@ struct pdmp_ensemble {
         cudaSetDevice(device);
         cudaDeviceSynchronize();
         void* bufs[] = {d_xc0, d_xd0, d_replay, d_sample, d_stats, d_hist, d_ctl, d_blkhist, d_segtab,
-                        d_nrec, d_njumps, d_nrej, d_status, d_offsets, d_time, d_xc, d_xd};
+                        d_nrec, d_njumps, d_nrej, d_status, d_offsets, d_time, d_xc, d_xd, d_st_time, d_st_xc, d_st_xd};
         for (void* b : bufs) if (b) cudaFree(b);
         for (int q = 0; q < NS; ++q) { if (d_pool[q]) cudaFree(d_pool[q]); if (d_scan[q]) cudaFree(d_scan[q]); }
         cudaEvent_t evs[] = {ev_fork, ev_kbeg, ev_h2d[0], ev_h2d[1], ev_d2h[0], ev_d2h[1]};
@@ -185,24 +202,30 @@ int32_t pdmp_device_count(void) {
     return n;
 }
 
-int32_t pdmp_model_count(void) { return (int32_t)registry().size(); }
+int32_t pdmp_model_count(void) { return (int32_t)(registry().size() + exact_registry().size()); }
 int32_t pdmp_model_info_by_id(int32_t id, pdmp_model_info* out) {
-    if (!out || id < 0 || id >= (int)registry().size()) return fail(PDMP_ERR_MODEL, "unknown model id");
-    *out = registry()[id].info;
+    if (!out || id < 0 || id >= pdmp_model_count()) return fail(PDMP_ERR_MODEL, "unknown model id");
+    *out = id < (int)registry().size() ? registry()[id].info : exact_info(id - (int)registry().size());
     return PDMP_OK;
 }
 int32_t pdmp_model_lookup(const char* name, pdmp_model_info* out) {
     if (!name || !out) return fail(PDMP_ERR_INVALID, "null argument");
     for (const auto& e : registry())
         if (std::strcmp(e.info.name, name) == 0) { *out = e.info; return PDMP_OK; }
+    for (size_t k = 0; k < exact_registry().size(); ++k)
+        if (std::strcmp(exact_registry()[k].name, name) == 0) { *out = exact_info((int)k); return PDMP_OK; }
     return fail(PDMP_ERR_MODEL, std::string("unknown model '") + name + "'");
 }
 
 int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_ensemble** out) {
     if (!d || !o || !out) return fail(PDMP_ERR_INVALID, "null argument");
     *out = nullptr;
+    if (d->model_id >= (int)registry().size() && d->model_id < pdmp_model_count())
+        return fail(PDMP_ERR_UNSUPPORTED, "exact-flow models run through pdmp_solve_ensemble (no resident handle)");
     if (d->model_id < 0 || d->model_id >= (int)registry().size()) return fail(PDMP_ERR_MODEL, "unknown model id");
     const ModelEntry& m = registry()[d->model_id];
+    if (o->algorithm == PDMP_ALG_REJECTION_EXACT)
+        return fail(PDMP_ERR_MODEL, std::string("model '") + m.info.name + "' has no exact flow: use CHV or Rejection");
     const int NC = m.info.n_c, ND = m.info.n_d, NR = m.info.n_r;
     if (o->n_jumps < 1) return fail(PDMP_ERR_INVALID, "n_jumps must be >= 1 and finite");
     if (!(d->t0 < d->tf)) return fail(PDMP_ERR_INVALID, "tspan must satisfy t0 < tf");
@@ -714,9 +737,142 @@ int32_t pdmp_ensemble_stats_device(pdmp_ensemble* e, void** stats_f64, uint64_t*
 
 void pdmp_ensemble_destroy(pdmp_ensemble* e) { delete e; }
 
+
+// ---- PDMP_ALG_REJECTION_EXACT: one synchronous call (src/rejection.jl:3-91 for n_traj trajectories) ----
+static int solve_exact(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_result* r) {
+    const ExactEntry& x = exact_registry()[d->model_id - (int)registry().size()];
+    const int N = x.n;
+    if (o->algorithm != PDMP_ALG_REJECTION_EXACT)
+        return fail(PDMP_ERR_MODEL, std::string("model '") + x.name + "' is an exact flow: use RejectionExact");
+    if (o->n_jumps < 1) return fail(PDMP_ERR_INVALID, "n_jumps must be >= 1 and finite");
+    if (!(d->t0 < d->tf)) return fail(PDMP_ERR_INVALID, "tspan must satisfy t0 < tf");
+    if (d->n_parms < x.n_parms || d->n_parms > MAXP) return fail(PDMP_ERR_MODEL, "number of parameters");
+    if (!d->xc0 || !d->xd0 || !d->nu) return fail(PDMP_ERR_INVALID, "null problem array");
+    for (size_t i = 0; i < (size_t)N * N; ++i)
+        if (d->nu[i] != 0) return fail(PDMP_ERR_UNSUPPORTED, "exact-flow models carry their jumps in Delta: nu must be all zero");
+    if (o->n_sample_times) return fail(PDMP_ERR_UNSUPPORTED, "sample_times are not available with RejectionExact");
+    if (o->precision != PDMP_PREC_FP64) return fail(PDMP_ERR_UNSUPPORTED, "RejectionExact is FP64 only");
+    if (o->rng_mode == PDMP_RNG_REPLAY && (!o->replay_u || !o->replay_stride)) return fail(PDMP_ERR_INVALID, "replay_u");
+    if (d->n_traj > 0xfffffff0ull) return fail(PDMP_ERR_INVALID, "n_traj per call must be < 2^32");
+    if (pdmp_device_count() <= o->device || o->device < 0)
+        return fail(PDMP_ERR_NO_DEVICE, "no usable CUDA device (this engine has no CPU fallback)");
+    CK(cudaSetDevice(o->device));
+    const size_t n = d->n_traj;
+    const int kc = o->save_c_count > 0 ? std::min(o->save_c_count, N) : N;
+    const int kd = o->save_d_count > 0 ? std::min(o->save_d_count, N) : N;
+    const unsigned long long cap = (unsigned long long)o->n_jumps;      // a trajectory saves at most n_jumps points
+    const size_t rec_bytes = 8 + 8 * (size_t)kc + 8 * (size_t)kd;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if ((double)n * (double)cap * (double)rec_bytes * 2.0 > 0.9 * (double)free_b)
+        return fail(PDMP_ERR_CAPACITY, "n_traj * n_jumps saved points of " + std::to_string(rec_bytes) +
+                                           " B exceed the device memory: lower save_c_count / save_d_count or shard the ensemble");
+
+    auto* e = new pdmp_ensemble();
+    std::unique_ptr<pdmp_ensemble> guard(e);
+    e->device = o->device; e->o = *o; e->n = n;
+    for (auto& st : e->cs) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaStream_t st = e->cs[0];
+    cudaEvent_t ev[4];
+    for (auto& v : ev) CK(cudaEventCreate(&v));
+    KParams& P = e->P;
+    P.n_traj = n; P.traj_id_offset = d->traj_id_offset;
+    P.xc0_per_traj = d->xc0_per_traj; P.xd0_per_traj = d->xd0_per_traj;
+    for (int i = 0; i < MAXP; ++i) P.parms[i] = i < d->n_parms ? d->parms[i] : 0.0;
+    P.t0 = d->t0; P.tf = d->tf; P.n_jumps = o->n_jumps;
+    P.rng_mode = o->rng_mode; P.seed = o->seed; P.replay_stride = o->replay_stride;
+    const size_t nxc = (size_t)(d->xc0_per_traj ? n : 1) * N, nxd = (size_t)(d->xd0_per_traj ? n : 1) * N;
+    for (size_t i = 0; i < nxd; ++i)
+        if (d->xd0[i] > 0x3fffffffLL || d->xd0[i] < -0x3fffffffLL) return fail(PDMP_ERR_INVALID, "xd0 entries must fit in 31 bits");
+    CK(cudaMalloc(&e->d_xc0, nxc * sizeof(double)));
+    CK(cudaMalloc(&e->d_xd0, nxd * sizeof(long long)));
+    CK(cudaMemcpyAsync(e->d_xc0, d->xc0, nxc * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_xd0, d->xd0, nxd * sizeof(long long), cudaMemcpyHostToDevice, st));
+    P.xc0 = e->d_xc0; P.xd0 = e->d_xd0;
+    if (o->rng_mode == PDMP_RNG_REPLAY) {
+        const size_t nr = n * o->replay_stride;
+        CK(cudaMalloc(&e->d_replay, std::max<size_t>(nr, 1) * sizeof(double)));
+        CK(cudaMemcpyAsync(e->d_replay, o->replay_u, nr * sizeof(double), cudaMemcpyHostToDevice, st));
+        P.replay_u = e->d_replay;
+    }
+    CK(cudaMalloc(&e->d_ctl, CTL_N * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(e->d_ctl, 0, CTL_N * sizeof(unsigned long long), st));
+    P.cursor = e->d_ctl; P.counters = e->d_ctl + CTL_CT;
+    CK(cudaMalloc(&e->d_nrec, (n + 1) * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(e->d_nrec, 0, (n + 1) * sizeof(unsigned long long), st));
+    CK(cudaMalloc(&e->d_njumps, std::max<size_t>(n, 1) * sizeof(long long)));
+    CK(cudaMalloc(&e->d_nrej, std::max<size_t>(n, 1) * sizeof(long long)));
+    CK(cudaMalloc(&e->d_status, std::max<size_t>(n, 1)));
+    P.nrec = e->d_nrec; P.njumps = e->d_njumps; P.nrejected = e->d_nrej; P.status = e->d_status;
+    const size_t slots = std::max<size_t>(n * cap, 1);
+    CK(cudaMalloc(&e->d_st_time, slots * sizeof(double)));
+    CK(cudaMalloc(&e->d_st_xc, slots * kc * sizeof(double)));
+    CK(cudaMalloc(&e->d_st_xd, slots * kd * sizeof(long long)));
+    ExactOut O{e->d_st_time, e->d_st_xc, e->d_st_xd, cap, kc, kd};
+
+    int bps = 0, sms = 0;
+    CK(x.occupancy(&bps));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(bps, 1) * sms, (n + 3) / 4));
+    CK(cudaEventRecord(ev[0], st));
+    if (n) CK(x.launch(P, O, grid, st));
+    CK(cudaEventRecord(ev[1], st));
+    // strided -> CSR
+    CK(cudaMalloc(&e->d_offsets, (n + 1) * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(e->d_offsets, 0, sizeof(unsigned long long), st));
+    unsigned long long total = 0;
+    if (n) {
+        size_t scan_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, e->d_nrec, e->d_offsets, (long long)(n + 1), st));
+        CK(cudaMalloc(&e->d_scan[0], std::max<size_t>(scan_bytes, 16)));
+        CK(cub::DeviceScan::ExclusiveSum(e->d_scan[0], scan_bytes, e->d_nrec, e->d_offsets, (long long)(n + 1), st));   // nrec[n] = 0
+        CK(cudaMemcpyAsync(&total, e->d_offsets + n, sizeof(total), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    CK(cudaMalloc(&e->d_time, std::max<size_t>(total, 1) * sizeof(double)));
+    CK(cudaMalloc(&e->d_xc, std::max<size_t>(total * kc, 1) * sizeof(double)));
+    CK(cudaMalloc((void**)&e->d_xd, std::max<size_t>(total * kd, 1) * sizeof(long long)));
+    CK(cudaEventRecord(ev[2], st));
+    if (n) {
+        exact_compact_kernel<<<(int)std::min<size_t>((n + 3) / 4, (size_t)sms * 16), 128, 0, st>>>(
+            P, O, e->d_offsets, e->d_time, e->d_xc, (long long*)e->d_xd);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ev[3], st));
+    // results to pinned staging owned by `e`
+    CK(e->h_offsets.reserve(n + 1)); CK(e->h_njumps.reserve(n)); CK(e->h_nrej.reserve(n)); CK(e->h_status.reserve(n));
+    CK(e->h_time.reserve(total)); CK(e->h_xc.reserve(total * kc)); CK(e->h_xd.reserve(total * kd * 8)); CK(e->h_ctl.reserve(CTL_N));
+    CK(cudaMemcpyAsync(e->h_offsets.p, e->d_offsets, (n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (n) {
+        CK(cudaMemcpyAsync(e->h_njumps.p, e->d_njumps, n * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(e->h_nrej.p, e->d_nrej, n * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(e->h_status.p, e->d_status, n, cudaMemcpyDeviceToHost, st));
+    }
+    if (total) {
+        CK(cudaMemcpyAsync(e->h_time.p, e->d_time, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(e->h_xc.p, e->d_xc, total * kc * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(e->h_xd.p, e->d_xd, total * kd * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(e->h_ctl.p, e->d_ctl, CTL_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float kms = 0, cms = 0;
+    CK(cudaEventElapsedTime(&kms, ev[0], ev[1])); CK(cudaEventElapsedTime(&cms, ev[2], ev[3]));
+    for (auto& v : ev) cudaEventDestroy(v);
+    std::memset(r, 0, sizeof(*r));
+    r->n_traj = n; r->total_records = total; r->records_needed = total;
+    r->offsets = (uint64_t*)e->h_offsets.p; r->time = e->h_time.p; r->xc = e->h_xc.p; r->xd = e->h_xd.p;
+    r->njumps = (int64_t*)e->h_njumps.p; r->nrejected = (int64_t*)e->h_nrej.p; r->status = e->h_status.p;
+    r->total_jumps = e->h_ctl.p[CTL_CT + CT_JUMPS]; r->total_candidates = e->h_ctl.p[CTL_CT + CT_CANDS];
+    r->kernel_ms = kms; r->compact_ms = cms;
+    r->n_c = kc; r->n_d = kd; r->xd_bytes = 8; r->n_comp = kc + kd;
+    r->owner = guard.release();
+    return PDMP_OK;
+}
+
 int32_t pdmp_solve_ensemble(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_result* r) {
     if (!d || !o || !r) return fail(PDMP_ERR_INVALID, "null argument");
     std::memset(r, 0, sizeof(*r));
+    if (d->model_id >= (int)registry().size() && d->model_id < pdmp_model_count()) return solve_exact(d, o, r);
     pdmp_ensemble* e = nullptr;
     int rc = pdmp_ensemble_create(d, o, &e);
     if (rc) return rc;

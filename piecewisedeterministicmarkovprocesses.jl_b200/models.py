@@ -51,6 +51,13 @@ EXAMPLES = {
 }
 
 
+# examples/neuron_rejection_exact.jl:49-57: N = 100, xc0 = rand(N)*0.2 .+ 0.5 (Julia's seeded stream is not
+# reproducible here: numpy PCG64 seed 1234 instead), xd0 = zeros, all-zero nu (the jumps are in Delta)
+_N_MF = 100
+EXAMPLES["neuron_mf"] = dict(nu=_N_MF, xc0=list(np.random.default_rng(1234).random(_N_MF) * 0.2 + 0.5),
+                             xd0=[0] * _N_MF, parms=[0.1], tspan=(0.0, 10050.0), n_jumps=10000)
+
+
 def problem(name, **override):
     """PDMPProblem of a reference example; F/R/Delta are the device functor's name."""
     e = dict(EXAMPLES[name])

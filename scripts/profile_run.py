@@ -28,6 +28,15 @@ elif model == "tcp2d":
 elif model == "sir_rejection":
     pb = P.models.problem("sir_rejection")
     ens = P.Ensemble(pb, P.RejectionGPU("sir_rejection"), trajectories=n, n_jumps=1000, max_records=n * 260)
+if model == "neuron_mf":
+    # RejectionExact (one warp per trajectory): one-shot solves, no resident handle
+    pb = P.models.problem("neuron_mf")
+    for seed in (0, 1):
+        r = P.solve(pb, P.RejectionExactGPU("neuron_mf"), trajectories=n, n_jumps=1000, seed=seed, save_c_count=2, save_d_count=2)
+        c = r.counters
+        print(model, n, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in c.items()},
+              "jumps/s", c["total_jumps"] / (c["kernel_ms"] * 1e-3), "candidates/s", c["total_candidates"] / (c["kernel_ms"] * 1e-3))
+    sys.exit(0)
 for seed in (0, 1):
     ens.run(seed=seed)
     c = ens.counters()

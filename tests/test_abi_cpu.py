@@ -31,9 +31,9 @@ def test_exports_match_header(P, lib):
 
 def test_struct_sizes(P):
     # natural C layout, no surprises: sizes are multiples of 8 and match the field sums
-    assert C.sizeof(P._abi.ModelInfo) == 8 * 4 + 32
+    assert C.sizeof(P._abi.ModelInfo) == 10 * 4 + 32
     assert C.sizeof(P._abi.ProblemDesc) == 8 * 8 + 4 * 6
-    assert C.sizeof(P._abi.SolveOpts) == 8 * 12 + 4 * 14
+    assert C.sizeof(P._abi.SolveOpts) == 8 * 12 + 4 * 16
     assert C.sizeof(P._abi.Result) == 8 * 3 + 8 * 11 + 8 * 5 + 8 * 4 + 4 * 8 + 8
 
 

@@ -588,3 +588,43 @@ def test_rejection_counts_do_not_depend_on_the_ode_pair(G):
         b = G.solve(pb, G.RejectionGPU(model, ode="tsit5"), trajectories=400, n_jumps=nj, replay=U)
         assert np.array_equal(a.njumps, b.njumps) and np.array_equal(a.nrejected, b.nrejected), model
         assert np.array_equal(a.xd, b.xd) and np.allclose(a.time, b.time, rtol=1e-5, atol=1e-7), model
+
+
+# ---- RejectionExact: one warp per trajectory (csrc/exact_kernel.cuh) ------------------------------------
+
+def test_rejection_exact_parity(G, orc):
+    from test_oracle_golden import rejection_exact_python
+    pb = G.models.problem("neuron_mf")
+    n, nj = 96, 80
+    U = uniforms(31, n, 12000)
+    rng = np.random.default_rng(2)
+    xc0 = 0.5 + 0.2 * rng.random((n, 100))
+    kw = dict(trajectories=n, n_jumps=nj, replay=U, xc0=xc0)
+    g = G.solve(pb, G.RejectionExactGPU("neuron_mf"), **kw)
+    c = orc.solve(pb, "neuron_mf", algorithm="rejection_exact", **kw)
+    same_discrete(g, c)
+    assert g.xd.shape == (n * nj, 100) and g.xd.dtype == np.int64
+    assert np.max(np.abs(g.time - c.time)) < 1e-10 and np.max(np.abs(g.xc - c.xc)) < 1e-11
+    t, xc, xd, nsteps, nrej = rejection_exact_python(xc0[5], pb.xd0, pb.tspan, nj, U[5])
+    assert np.array_equal(g[5].xd.T, xd) and g.nrejected[5] == nrej and np.max(np.abs(g[5].time - t)) < 1e-10
+    assert g.counters["total_jumps"] == int((g.njumps - 1).sum()) and np.all(g.status == G._abi.ST_HIT_NJUMPS)
+    # Philox mode: same trajectories as the oracle's Philox stream; shards reproduce the whole; partial saving
+    kw = dict(trajectories=64, n_jumps=300, seed=9, save_c_count=2, save_d_count=2)
+    g = G.solve(pb, G.RejectionExactGPU("neuron_mf"), **kw)
+    c = orc.solve(pb, "neuron_mf", algorithm="rejection_exact", **kw)
+    same_discrete(g, c)
+    assert g.xc.shape == (64 * 300, 2) and np.max(np.abs(g.time - c.time)) < 1e-9
+    h = G.solve(pb, G.RejectionExactGPU("neuron_mf"), trajectories=24, traj_id_offset=40, n_jumps=300, seed=9,
+                save_c_count=2, save_d_count=2)
+    assert np.array_equal(h.njumps, g.njumps[40:]) and np.array_equal(h.time, g.time[40 * 300:])
+    # tf reached before the cap: OK status, last point at tf
+    pb.tspan[1] = 2.0
+    g = G.solve(pb, G.RejectionExactGPU("neuron_mf"), trajectories=32, n_jumps=100000, seed=1, save_c_count=1, save_d_count=1)
+    c = orc.solve(pb, "neuron_mf", algorithm="rejection_exact", trajectories=32, n_jumps=100000, seed=1, save_c_count=1, save_d_count=1)
+    same_discrete(g, c)
+    assert np.all(g.status == G._abi.ST_OK) and np.all(g.time[g.offsets[1:].astype(np.int64) - 1] == 2.0)
+    # wrong pairings are refused
+    with pytest.raises(G.PDMPError):
+        G.solve(pb, G.RejectionGPU("neuron_mf"), trajectories=2, n_jumps=10)
+    with pytest.raises(G.PDMPError):
+        G.solve(G.models.problem("tcp"), G.RejectionExactGPU("tcp"), trajectories=2, n_jumps=10)

@@ -210,3 +210,59 @@ def test_rates_cst_closed_form(orc, P):
     r = orc.solve(pb, "rates_cst", algorithm="chv", ode="tsit5", n_jumps=14, replay=U, reltol=1e-10, abstol=1e-12)
     assert np.max(np.abs(r.time - _rates_cst_closed_form(U, 14))) < 1e-10
     assert np.array_equal(r.xd[:, 0], np.arange(14)) and np.all(r.xd[:, 1] == 0)
+
+
+# ---- RejectionExact (reference src/rejection.jl:3-91, examples/neuron_rejection_exact.jl) -----------
+
+def rejection_exact_python(xc0, xd0, tspan, n_jumps, U):
+    """Independent restatement in plain numpy of `solve(problem, Flow)` for the mean-field neuron
+    network, written from the Julia (src/rejection.jl:3-91), consuming the uniforms U in order."""
+    N = len(xc0)
+    f = lambda x: x ** 8
+    bound = N * f(1.201)
+    it = iter(U)
+    x, xd, (t, tf) = np.array(xc0, float), np.array(xd0, np.int64), tspan
+    dte = -np.log(next(it))
+    time, XC, XD, nsteps, nrej = [t], [x.copy()], [xd.copy()], 1, 0
+    while t < tf and nsteps < n_jumps:
+        reject = True
+        while reject and nsteps < n_jumps:
+            t1 = min(tf, t + dte / bound)
+            xbar = x.sum() / N
+            x = xbar + np.exp(-0.24 * (t1 - t)) * (x - xbar)
+            t = t1
+            tot = f(x).sum()
+            assert tot <= bound
+            reject = False if t == tf else (next(it) < 1 - tot / bound)
+            dte = -np.log(next(it))
+            nrej += reject
+        rate = f(x)
+        if t < tf:
+            thr = next(it) * rate.sum()
+            ev = int(min(np.searchsorted(np.cumsum(rate), thr, side="left"), N - 1))   # first i with !(cw_i < thr)
+            x = x + 0.98 / N
+            x[ev] = 0.0
+            xd[ev] += 1
+        nsteps += 1
+        time.append(t); XC.append(x.copy()); XD.append(xd.copy())
+    return np.array(time), np.array(XC), np.array(XD), nsteps, nrej
+
+
+def test_rejection_exact_oracle_vs_plain_restatement(orc, P):
+    pb = P.models.problem("neuron_mf")
+    assert pb.nu.shape == (100, 100) and not pb.nu.any()
+    U = np.clip(np.random.default_rng(5).random(20000), 2.0 ** -53, 1 - 2.0 ** -53)
+    r = orc.solve(pb, "neuron_mf", algorithm="rejection_exact", n_jumps=60, replay=U)
+    t, xc, xd, nsteps, nrej = rejection_exact_python(pb.xc0, pb.xd0, pb.tspan, 60, U)
+    assert r.njumps[0] == nsteps == 60 and r.nrejected[0] == nrej and len(r.time) == 60
+    assert np.array_equal(r.xd, xd) and r.xd.shape == (60, 100)          # all N components are saved (src/rejection.jl:32)
+    assert np.max(np.abs(r.time - t)) < 1e-12 and np.max(np.abs(r.xc - xc)) < 1e-12
+    # the mean of xc is constant along the flow and moves by J/N - x_ev/N at a jump; a spike resets its neuron
+    k = orc.solve(pb, "neuron_mf", algorithm="rejection_exact", n_jumps=60, replay=U, save_c_count=2, save_d_count=3)
+    assert k.xc.shape == (60, 2) and k.xd.shape == (60, 3) and np.array_equal(k.xd, xd[:, :3])
+    # a horizon shorter than the jumps: the last point sits at tf, with no jump there (src/rejection.jl:64-65,78)
+    pb.tspan[1] = 1.0
+    s = orc.solve(pb, "neuron_mf", algorithm="rejection_exact", n_jumps=60, replay=U)
+    t2, _, xd2, n2, nrej2 = rejection_exact_python(pb.xc0, pb.xd0, pb.tspan, 60, U)
+    assert s.time[-1] == 1.0 and s.njumps[0] == n2 and s.nrejected[0] == nrej2 and np.array_equal(s.xd, xd2)
+    assert s.status[0] == P._abi.ST_OK and r.status[0] == P._abi.ST_HIT_NJUMPS
