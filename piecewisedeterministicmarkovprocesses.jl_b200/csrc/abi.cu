@@ -813,7 +813,8 @@ static int solve_exact(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdm
     int bps = 0, sms = 0;
     CK(x.occupancy(&bps));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(bps, 1) * sms, (n + 3) / 4));
+    const size_t per_cta = (size_t)4 * (32 / x.group);   // trajectories a CTA holds at a time
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(bps, 1) * sms, (n + per_cta - 1) / per_cta));
     CK(cudaEventRecord(ev[0], st));
     if (n) CK(x.launch(P, O, grid, st));
     CK(cudaEventRecord(ev[1], st));

@@ -6,11 +6,11 @@
 // for models with MANY continuous variables (examples/neuron_rejection_exact.jl: N = 100 neurons,
 // one rate and one discrete counter per neuron).  Such a state does not fit one thread's
 // registers, and there is no ODE to integrate, so the parallel shape differs from
-// ensemble_kernel.cuh: ONE WARP PER TRAJECTORY.  Lane l holds components PER*l .. PER*l+PER-1
-// (blocked, so that prefix sums run in index order) in registers; totals, the empirical mean and the
-// categorical draw over N rates are warp reductions / a warp prefix scan; the uniforms are computed
-// redundantly by every lane (a warp instruction costs the same for 1 or 32 lanes, and no shuffle is
-// needed).  Warps pull trajectories from the global cursor like the lanes of the other kernel.
+// ensemble_kernel.cuh: a GROUP OF G LANES PER TRAJECTORY (G = 8: four trajectories per warp).  Lane l
+// of a group holds components PER*l .. PER*l+PER-1 (blocked, so that prefix sums run in index order)
+// in registers; totals, the empirical mean and the categorical draw over N rates are group
+// reductions / a group prefix scan (shuffles); the uniforms are computed redundantly by every lane
+// of the group (no shuffle needed).  Groups pull trajectories from the global cursor.
 //
 // An exact-flow model provides
 //     static constexpr int N, NP;  static constexpr const char* NAME;
@@ -19,21 +19,39 @@
 //     bound(p)                       constant bound on the total   R(...)[2]
 //     delta(x, xd, p, t, ev, W)      the jump                      Delta(xc, xd, parms, t, ind_reaction)
 // where W gives the lane's view: W.idx(j) = global index of the lane's j-th component, W.valid(j),
-// W.sum(v) = warp sum of a lane-local value.
+// W.sum(v) = group sum of a lane-local value.
 #pragma once
 #include "ensemble_kernel.cuh"
 
 namespace pdmp {
 
-template <int N_>
-struct WarpView {
-    static constexpr int N = N_, PER = (N_ + 31) / 32;
-    unsigned lane;
-    PDMP_DEV int idx(int j) const { return (int)lane * PER + j; }
+// A trajectory is held by a GROUP of G lanes (G = 8, 16 or 32; 32 / G trajectories per warp): the
+// scalar part of a candidate (one Philox block, a log, an exp, two divisions: ~2/3 of its
+// instructions) is the same for every lane of a group, so narrow groups amortise it over several
+// trajectories per warp instruction.  Every lane of a group carries the group's scalars redundantly.
+template <int N_, int G_>
+struct GroupView {
+    static constexpr int N = N_, G = G_, PER = (N_ + G_ - 1) / G_;
+    unsigned gl;      // lane within the group
+    unsigned gmask;   // the group's lanes: shuffles stay legal when groups diverge from each other
+    PDMP_DEV int idx(int j) const { return (int)gl * PER + j; }
     PDMP_DEV bool valid(int j) const { return idx(j) < N; }
-    PDMP_DEV static double sum(double v) {
+    PDMP_DEV double sum(double v) const {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+        return v;
+    }
+    PDMP_DEV int min_(int v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(gmask, v, o));
+        return v;
+    }
+    PDMP_DEV double scan_incl(double v) const {   // inclusive prefix sum over the group's lanes
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            const double u = __shfl_up_sync(gmask, v, o, G);
+            if ((int)gl >= o) v += u;
+        }
         return v;
     }
 };
@@ -46,114 +64,116 @@ struct ExactOut {
     int kc, kd;
 };
 
-template <class M>
+// The reference's two nested loops (src/rejection.jl:49-52) are flattened: one loop iteration = one
+// candidate for every live group; the accepted branch (jump, save, nsteps += 1: 1 candidate in ~35
+// for the neuron example) and the (re)initialisation are predicated rare events.
+template <class M, int G>
 __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ KParams P, const ExactOut O) {
-    using W = WarpView<M::N>;
+    using W = GroupView<M::N, G>;
     constexpr int PER = W::PER, N = M::N;
-    W w{threadIdx.x & 31u};
-    const unsigned lane = w.lane;
+    const unsigned lane = threadIdx.x & 31u;
+    W w{lane % G, (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane - lane % G)};
+    const int leader = (int)(lane - w.gl);
     unsigned long long c_cands = 0, c_jumps = 0;
 
-    for (;;) {
-        unsigned long long idx = 0;
-        if (lane == 0) idx = atomicAdd(P.cursor, 1ull);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= P.n_traj) break;
+    double x[PER];
+    int xd[PER];
+    DrawStream rng;
+    unsigned long long idx = 0;
+    double t = 0.0, dte = 0.0;
+    long long nsteps = 0, nrej = 0;
+    bool need_init = true, dead = false, ex = false;
+    const double bnd = M::bound(P.parms);                                           // ppf[2]
 
-        // ---- init!(problem) + the set-up of src/rejection.jl:8-47 ----
-        double x[PER];
-        int xd[PER];
+    auto draw = [&]() {
+        return rng.next(P.rng_mode, P.replay_u + (size_t)idx * P.replay_stride, P.replay_stride,
+                        P.traj_id_offset + idx, P.seed, ex);
+    };
+    auto save = [&](unsigned long long k) {          // _push_time! / push!(xc_hist) / push!(xd_hist), :87-89
+        if (k >= O.cap) return;
+        const size_t at = (size_t)idx * O.cap + k;
+        if (w.gl == 0) O.time[at] = t;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            const int i = w.valid(j) ? w.idx(j) : 0;
-            x[j] = w.valid(j) ? P.xc0[(P.xc0_per_traj ? (size_t)idx * N : 0) + i] : 0.0;
-            xd[j] = w.valid(j) ? (int)P.xd0[(P.xd0_per_traj ? (size_t)idx * N : 0) + i] : 0;
+            const int i = w.idx(j);
+            if (w.valid(j) && i < O.kc) O.xc[at * O.kc + i] = x[j];
+            if (w.valid(j) && i < O.kd) O.xd[at * O.kd + i] = (long long)xd[j];
         }
-        DrawStream rng; rng.init();
-        bool ex = false;
-        auto draw = [&]() {
-            return rng.next(P.rng_mode, P.replay_u + (size_t)idx * P.replay_stride, P.replay_stride,
-                            P.traj_id_offset + idx, P.seed, ex);
-        };
-        double t = P.t0;
-        double dte = -log(draw());                       // simjptimes.tstop_extended (src/problem.jl:153)
-        const double bnd = M::bound(P.parms);            // ppf[2]
-        long long nsteps = 1, nrej = 0;
-        int status = PDMP_ST_OK;
-        const size_t base = (size_t)idx * O.cap;
-        auto save = [&](unsigned long long k) {          // _push_time! / push!(xc_hist) / push!(xd_hist)
-            if (k >= O.cap) return;
-            if (lane == 0) O.time[base + k] = t;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const int i = w.idx(j);
-                if (w.valid(j) && i < O.kc) O.xc[(base + k) * O.kc + i] = x[j];
-                if (w.valid(j) && i < O.kd) O.xd[(base + k) * O.kd + i] = (long long)xd[j];
-            }
-        };
-        save(0);
-
-        while (t < P.tf && nsteps < P.n_jumps && status == PDMP_ST_OK) {          // :49
-            bool reject = true;
-            double rate[PER], tot = 0.0;
-            while (reject && nsteps < P.n_jumps) {                                  // :52
-                const double t1 = fmin(P.tf, t + dte / bnd);                        // :53
-                M::flow(x, xd, P.parms, t, t1, w);                                  // :54-58
-                t = t1;
-                double loc = 0.0;
-#pragma unroll
-                for (int j = 0; j < PER; ++j) {
-                    rate[j] = w.valid(j) ? M::rate(x[j], xd[j], P.parms, t) : 0.0;
-                    loc += rate[j];
-                }
-                tot = W::sum(loc);                                                  // ppf[1], :62
-                ++c_cands;
-                if (!(tot <= bnd)) { status = PDMP_ST_BOUND_VIOLATED; break; }      // @assert :63
-                if (t == P.tf) reject = false;                                      // :64-65
-                else reject = draw() < 1.0 - tot / bnd;                             // :67
-                dte = -log(draw());                                                 // :69
-                if (reject) ++nrej;                                                 // :70-72
-                if (ex) { status = PDMP_ST_REPLAY_EXHAUSTED; break; }
-            }
-            if (status != PDMP_ST_OK) break;
-            if (t < P.tf && !reject) {                                              // :78
-                // pfsample over the N rates (src/utils.jl:46-57): inclusive prefix sums in index order
-                const double thr = draw() * tot;
-                double run = 0.0, incl[PER];
-#pragma unroll
-                for (int j = 0; j < PER; ++j) { run += rate[j]; incl[j] = run; }
-                double scan = run;                                                  // warp inclusive scan of lane totals
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double v = __shfl_up_sync(0xffffffffu, scan, o);
-                    if ((int)lane >= o) scan += v;
-                }
-                const double excl = scan - run;
-                // first index whose inclusive sum is not < thr; the last index absorbs round-off
-                int mine = N;                                                       // 1-based candidates, N = fallback
-#pragma unroll
-                for (int j = PER - 1; j >= 0; --j)
-                    if (w.valid(j) && !(excl + incl[j] < thr)) mine = w.idx(j) + 1;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
-                M::delta(x, xd, P.parms, t, mine, w);                               // affect!, :83
-                ++c_jumps;
-                if (ex) { status = PDMP_ST_REPLAY_EXHAUSTED; break; }
-            }
-            save((unsigned long long)nsteps);                                       // :87-89
-            ++nsteps;                                                               // :86
-        }
-        if (lane == 0) {
-            if (status == PDMP_ST_OK && t < P.tf) status = PDMP_ST_HIT_NJUMPS;
-            if (status != PDMP_ST_BOUND_VIOLATED && status != PDMP_ST_REPLAY_EXHAUSTED && (unsigned long long)nsteps > O.cap)
-                status = PDMP_ST_OUTPUT_OVERFLOW;
+    };
+    auto finish = [&](int status) {
+        if (w.gl == 0) {
             P.nrec[idx] = (unsigned long long)min((unsigned long long)nsteps, O.cap);
             P.njumps[idx] = nsteps;                                                 // PDMPResult(..., nsteps, n_reject), :90
             P.nrejected[idx] = nrej;
             P.status[idx] = (unsigned char)status;
         }
+        need_init = true;
+    };
+
+    for (;;) {
+        __syncwarp();
+        if (need_init && !dead) {
+            // ---- init!(problem) + the set-up of src/rejection.jl:8-47 ----
+            unsigned long long nx = 0;
+            if (w.gl == 0) nx = atomicAdd(P.cursor, 1ull);
+            idx = __shfl_sync(w.gmask, nx, leader);
+            if (idx >= P.n_traj) dead = true;
+            else {
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const int i = w.valid(j) ? w.idx(j) : 0;
+                    x[j] = w.valid(j) ? P.xc0[(P.xc0_per_traj ? (size_t)idx * N : 0) + i] : 0.0;
+                    xd[j] = w.valid(j) ? (int)P.xd0[(P.xd0_per_traj ? (size_t)idx * N : 0) + i] : 0;
+                }
+                rng.init(); ex = false;
+                t = P.t0; nsteps = 1; nrej = 0;
+                dte = -log(draw());                                                 // tstop_extended, src/problem.jl:153
+                save(0);
+                need_init = false;
+                if (!(t < P.tf && nsteps < P.n_jumps)) finish(t < P.tf ? PDMP_ST_HIT_NJUMPS : PDMP_ST_OK);   // :49
+            }
+        }
+        if (__all_sync(0xffffffffu, dead)) break;
+        if (dead || need_init) continue;
+
+        // ---- one candidate, src/rejection.jl:53-72 ----
+        const double t1 = fmin(P.tf, t + dte / bnd);
+        M::flow(x, xd, P.parms, t, t1, w);
+        t = t1;
+        double loc = 0.0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) loc += w.valid(j) ? M::rate(x[j], xd[j], P.parms, t) : 0.0;
+        const double tot = w.sum(loc);                                              // ppf[1]
+        ++c_cands;
+        if (!(tot <= bnd)) { finish(PDMP_ST_BOUND_VIOLATED); continue; }            // @assert :63
+        bool reject;
+        if (t == P.tf) reject = false;                                              // :64-65
+        else reject = draw() < 1.0 - tot / bnd;                                     // :67
+        dte = -log(draw());                                                         // :69
+        if (ex) { finish(PDMP_ST_REPLAY_EXHAUSTED); continue; }
+        if (reject) { ++nrej; continue; }                                           // :70-72
+
+        // ---- accepted: the jump (:76-84), then nsteps += 1 and the saved point (:86-89) ----
+        if (t < P.tf) {
+            // pfsample over the N rates (src/utils.jl:46-57): inclusive prefix sums in index order
+            const double thr = draw() * tot;
+            double run = 0.0, incl[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { run += w.valid(j) ? M::rate(x[j], xd[j], P.parms, t) : 0.0; incl[j] = run; }
+            const double excl = w.scan_incl(run) - run;
+            int mine = N;                              // first index whose inclusive sum is not < thr; N absorbs round-off
+#pragma unroll
+            for (int j = PER - 1; j >= 0; --j)
+                if (w.valid(j) && !(excl + incl[j] < thr)) mine = w.idx(j) + 1;
+            M::delta(x, xd, P.parms, t, w.min_(mine), w);                           // affect!, :83
+            ++c_jumps;
+            if (ex) { finish(PDMP_ST_REPLAY_EXHAUSTED); continue; }
+        }
+        save((unsigned long long)nsteps);
+        ++nsteps;
+        if (!(t < P.tf && nsteps < P.n_jumps)) finish(t < P.tf ? PDMP_ST_HIT_NJUMPS : PDMP_ST_OK);   // :49
     }
-    if (lane == 0) {
+    if (w.gl == 0) {
         if (c_cands) atomicAdd(P.counters + CT_CANDS, c_cands);
         if (c_jumps) atomicAdd(P.counters + CT_JUMPS, c_jumps);
     }
@@ -176,24 +196,32 @@ __global__ void __launch_bounds__(128) exact_compact_kernel(const KParams P, con
 }
 
 struct ExactEntry {
-    int n, n_parms;
+    int n, n_parms, group;   // group: lanes per trajectory
     const char* name;
     cudaError_t (*launch)(const KParams& P, const ExactOut& O, int grid, cudaStream_t st);
     cudaError_t (*occupancy)(int* blocks_per_sm);
 };
 template <class M>
 cudaError_t exact_launch(const KParams& P, const ExactOut& O, int grid, cudaStream_t st) {
-    exact_kernel<M><<<grid, 128, 0, st>>>(P, O);
+    exact_kernel<M, M::GROUP><<<grid, 128, 0, st>>>(P, O);
     return cudaGetLastError();
 }
 template <class M>
-cudaError_t exact_occupancy(int* out) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, exact_kernel<M>, 128, 0); }
+cudaError_t exact_occupancy(int* out) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, exact_kernel<M, M::GROUP>, 128, 0);
+}
 template <class M>
-ExactEntry make_exact_entry() { return ExactEntry{M::N, M::NP, M::NAME, &exact_launch<M>, &exact_occupancy<M>}; }
+ExactEntry make_exact_entry() {
+    return ExactEntry{M::N, M::NP, M::GROUP, M::NAME, &exact_launch<M>, &exact_occupancy<M>};
+}
 
 // ---- examples/neuron_rejection_exact.jl: mean-field network of N = 100 neurons ---------------------
 struct NeuronMfDev {
     static constexpr int N = 100, NP = 1;
+#ifndef PDMP_EXACT_GROUP
+#define PDMP_EXACT_GROUP 8
+#endif
+    static constexpr int GROUP = PDMP_EXACT_GROUP;   // lanes per trajectory: 13 neurons per lane, 4 trajectories per warp
     static constexpr const char* NAME = "neuron_mf";
     // Phi: the empirical mean is constant between jumps; x_i relaxes to it at rate lambda = 0.24  (:12-20)
     template <class W>
@@ -201,7 +229,7 @@ struct NeuronMfDev {
         double loc = 0.0;
 #pragma unroll
         for (int j = 0; j < W::PER; ++j) loc += w.valid(j) ? x[j] : 0.0;
-        const double xbar = W::sum(loc) / (double)N;
+        const double xbar = w.sum(loc) / (double)N;
         const double e = exp(-0.24 * (t1 - t0));
 #pragma unroll
         for (int j = 0; j < W::PER; ++j) x[j] = xbar + e * (x[j] - xbar);
