@@ -97,6 +97,25 @@ struct DrawStream {
         cache = u01_from_bits(c2, c3);
         return u01_from_bits(c0, c1);
     }
+    // The next TWO draws with exactly one Philox call whatever the parity of idx (the same stream as two
+    // next() calls): draws k, k+1 need block (k+1)/2 only — for even k both halves of it, for odd k the
+    // cached half of the previous block and the first half of it.  Lanes whose idx parities differ
+    // (Rejection: 2 or 3 draws per candidate) therefore stay converged through the Philox rounds.
+    PDMP_DEV void next2(int rng_mode, const double* __restrict__ replay, uint64_t replay_len, uint64_t gid, uint64_t seed,
+                        bool& exhausted, double& u0, double& u1) {
+        const uint32_t k = idx;
+        idx += 2;
+        if (rng_mode == 1) {
+            if (k + 1 >= replay_len) { exhausted = true; u0 = u1 = 0.5; return; }
+            u0 = __ldg(replay + k); u1 = __ldg(replay + k + 1);
+            return;
+        }
+        uint32_t c0 = (uint32_t)gid, c1 = (uint32_t)(gid >> 32), c2 = (k + 1u) >> 1, c3 = 0u;
+        philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double a = u01_from_bits(c0, c1), b = u01_from_bits(c2, c3);
+        if (k & 1u) { u0 = cache; u1 = a; cache = b; }
+        else { u0 = a; u1 = b; }
+    }
 };
 
 // ---------------------------------------------------------------------------------------

@@ -440,8 +440,11 @@ struct Traj {
         for (int i = 1; i < NR; ++i) tot += rate[i];
         const R bnd = M::bound(y, xd, P.parms, (R)tc);
         if (!(tot < bnd)) { finish(P, PDMP_ST_BOUND_VIOLATED); return true; }  // @assert :33
-        const bool reject = draw(P, ex) < 1.0 - (double)tot / (double)bnd;   // :35
-        const double dtn = -log(draw(P, ex)) / (double)bnd;  // :36
+        double u_acc, u_exp;   // rand() of :35 then rand() of :36, one converged Philox call for both
+        rng.next2(P.rng_mode, P.replay_u + (size_t)lid * P.replay_stride, P.replay_stride, P.traj_id_offset + lid, P.seed,
+                  ex, u_acc, u_exp);
+        const bool reject = u_acc < 1.0 - (double)tot / (double)bnd;         // :35
+        const double dtn = -log(u_exp) / (double)bnd;                        // :36
         const bool fire = tc < P.tf && !reject;
         if (fire) {                                          // :41
             const R thr = (R)draw(P, ex) * tot;              // :55

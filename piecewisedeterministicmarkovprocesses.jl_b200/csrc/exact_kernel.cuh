@@ -147,9 +147,14 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ KPar
         ++c_cands;
         if (!(tot <= bnd)) { finish(PDMP_ST_BOUND_VIOLATED); continue; }            // @assert :63
         bool reject;
-        if (t == P.tf) reject = false;                                              // :64-65
-        else reject = draw() < 1.0 - tot / bnd;                                     // :67
-        dte = -log(draw());                                                         // :69
+        if (t == P.tf) { reject = false; dte = -log(draw()); }                      // :64-65, :69
+        else {
+            double u_acc, u_exp;   // rand() of :67 then rand() of :69: one Philox call whatever the parity
+            rng.next2(P.rng_mode, P.replay_u + (size_t)idx * P.replay_stride, P.replay_stride, P.traj_id_offset + idx,
+                      P.seed, ex, u_acc, u_exp);
+            reject = u_acc < 1.0 - tot / bnd;
+            dte = -log(u_exp);
+        }
         if (ex) { finish(PDMP_ST_REPLAY_EXHAUSTED); continue; }
         if (reject) { ++nrej; continue; }                                           // :70-72
 
