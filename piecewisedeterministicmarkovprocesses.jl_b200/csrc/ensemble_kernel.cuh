@@ -586,7 +586,9 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
         }
 
         // ---- RK: one adaptive attempt, clipped at the threshold (tstops) ----
-        if (st == LANE_RUN) {
+        // (compiled out when there is no flow: its registers would cap the occupancy of a kernel that
+        //  only ever runs the candidate section)
+        if constexpr (!NO_FLOW) if (st == LANE_RUN) {
             const double hprop = tr.h;
             double step = hprop;
             bool clipped = false;
