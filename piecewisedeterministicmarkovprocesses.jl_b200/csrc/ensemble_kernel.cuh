@@ -475,15 +475,20 @@ struct Traj {
     }
 };
 
-// resident CTAs per SM the kernel is compiled for: small models fit 6 x 128 threads in the
-// register file (<= 80 registers), medium ones 5 (<= 96), the larger ones 4 (<= 128 registers;
-// Morris-Lecar loses 10 % to spills at 96)
+// resident CTAs per SM the kernel is compiled for: small models run 6 x 128 threads (<= 80
+// registers), those with a hand-simplified CHV field (TCP) 7 x 128 (<= 72
+// registers; measured on TCP: 6 CTAs / 80 registers 54.4 ms, 7 / 72 53.0 ms, 8 / 64 53.9 ms — the
+// extra warps pay for a few spilled words), medium ones 5 (<= 96), the larger ones 4 (<= 128
+// registers; Morris-Lecar loses 10 % to spills at 96)
+#ifndef PDMP_MINB_SMALL
+#define PDMP_MINB_SMALL 7
+#endif
 template <class M, int ALG, class R>
 struct MinBlocks {
     static constexpr int D = (ALG == PDMP_ALG_CHV) ? M::NC + 1 : M::NC;
     static constexpr bool small = (D <= 2 && M::NR <= 2 && M::ND <= 2);
     static constexpr bool medium = (D <= 3 && M::NR <= 2 && M::ND <= 2);   // tcp2d: 96 registers, measured +8 %
-    static constexpr int value = sizeof(R) == 4 ? (small ? 7 : 5) : (small ? 6 : medium ? 5 : 4);
+    static constexpr int value = sizeof(R) == 4 ? (small ? 7 : 5) : (small ? (M::HAS_CHV_FIELD ? PDMP_MINB_SMALL : 6) : medium ? 5 : 4);
 };
 
 // lane states of the phase scheduler
