@@ -280,6 +280,50 @@ PDMP_DEV R rk_attempt(RHS&& f, const R (&u)[D], const R (&k1)[D], R t, R h, R (&
     return e2;
 }
 
+// The same attempt for a field of the form  f(u) = c * g(u)  with a SIGN vector c (c_i = +-1, constant
+// over the step) and a scalar g: every stage slope is c times a scalar, so ONE accumulation chain
+// serves all components (k_j[i] = c_i g_j exactly, hence sum_j a_sj k_j[i] = c_i sum_j a_sj g_j bit for
+// bit: the results are identical to rk_attempt, with about half the FMAs and a third of the stage
+// registers).  TCP in CHV variables is such a field: (F, 1) / Rtot = (+-1, 1) * x.
+template <class Tab, int D, class R, class G>
+PDMP_DEV R rk_attempt_signed(G&& g, const R (&c)[D], const R (&u)[D], R g1, R t, R h, R (&unew)[D], R& g7, R reltol,
+                             R abstol, R& inc_last) {
+    R gk[7], hc[D];
+    gk[0] = g1;
+#pragma unroll
+    for (int i = 0; i < D; ++i) hc[i] = h * c[i];
+#pragma unroll
+    for (int s = 1; s < 7; ++s) {
+        R acc = Tab::template A<R>(s - 1, 0) * gk[0];
+#pragma unroll
+        for (int j = 1; j < s; ++j)
+            if (Tab::a(s - 1, j) != 0.0) acc = fma(Tab::template A<R>(s - 1, j), gk[j], acc);
+        R us[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) us[i] = fma(hc[i], acc, u[i]);
+        if (s == 6) {
+            inc_last = h * acc;
+#pragma unroll
+            for (int i = 0; i < D; ++i) unew[i] = us[i];
+        }
+        gk[s] = g(us);
+    }
+    R acc = Tab::template BT<R>(0) * gk[0];
+#pragma unroll
+    for (int j = 1; j < 7; ++j)
+        if (Tab::bt(j) != 0.0) acc = fma(Tab::template BT<R>(j), gk[j], acc);
+    const R he = h * acc;
+    R e2 = R(0);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        const R sc = fma(fmax(fabs(u[i]), fabs(unew[i])), reltol, abstol);
+        const R r = he * rcp_weight(sc);
+        e2 = fma(r, r, e2);
+    }
+    g7 = gk[6];
+    return e2;
+}
+
 // ---------------------------------------------------------------------------------------
 // PI controller (OrdinaryDiffEq PIController defaults for order-5 pairs: beta1 = 7/50,
 // beta2 = 2/25, gamma = 9/10, qmin = 1/5, qmax = 10, qoldinit = 1e-4).  The powers are

@@ -82,6 +82,10 @@ struct RecLayout {
 template <class M, class = void> struct ConstRateOk { static constexpr bool value = false; };
 template <class M> struct ConstRateOk<M, decltype((void)M::CONST_RATE_OK)> { static constexpr bool value = M::CONST_RATE_OK; };
 
+// models whose CHV field is a sign vector times a scalar (TCP) use the single-chain RK attempt
+template <class M, class = void> struct ChvSigned { static constexpr bool value = false; };
+template <class M> struct ChvSigned<M, decltype((void)M::CHV_SIGNED_SCALAR)> { static constexpr bool value = M::CHV_SIGNED_SCALAR; };
+
 // geometric segment sizes: segment k holds REC_BLOCK << (k >> 2) records (4 segments per doubling)
 __host__ __device__ inline unsigned seg_records(int k) { return (unsigned)REC_BLOCK << (k >> 2); }
 
@@ -599,9 +603,18 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
             bool clipped = false;
             const double rem = tr.tstop - tr.s;
             if (step >= rem) { step = rem; clipped = true; }
-            R yn[D], k7[D], inc;
-            auto rhs = [&](const R* x, R* dx, R t) { tr.field(P, x, dx, t); };
-            const R e2 = rk_attempt<Tab, D, R>(rhs, tr.y, tr.k1, (R)tr.s, (R)step, yn, k7, (R)P.reltol, (R)P.abstol, inc);
+            R yn[D], k7[D], inc, e2;
+            if constexpr (ALG == PDMP_ALG_CHV && ChvSigned<M>::value) {
+                R c[D], g7;
+                M::chv_signs(c, tr.xd, P.parms);
+                e2 = rk_attempt_signed<Tab, D, R>([&](const R* x) { return M::chv_scalar(x, tr.xd, P.parms); }, c, tr.y,
+                                                  tr.k1[D - 1], (R)tr.s, (R)step, yn, g7, (R)P.reltol, (R)P.abstol, inc);
+#pragma unroll
+                for (int i = 0; i < D; ++i) k7[i] = c[i] * g7;
+            } else {
+                auto rhs = [&](const R* x, R* dx, R t) { tr.field(P, x, dx, t); };
+                e2 = rk_attempt<Tab, D, R>(rhs, tr.y, tr.k1, (R)tr.s, (R)step, yn, k7, (R)P.reltol, (R)P.abstol, inc);
+            }
             ++c_attempts;
             const bool accept = e2 <= (R)D;
             double hnext;
