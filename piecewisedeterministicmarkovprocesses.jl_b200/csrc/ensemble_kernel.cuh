@@ -594,10 +594,16 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
             continue;
         }
 
-        // ---- RK: one adaptive attempt, clipped at the threshold (tstops) ----
+        // ---- RK: adaptive attempts, clipped at the threshold (tstops), until enough lanes wait ----
+        // Lanes only LEAVE the running set in this phase, so the scheduler's decision reduces to one
+        // ballot per attempt; the full three-way test is redone when the threshold is reached.
         // (compiled out when there is no flow: its registers would cap the occupancy of a kernel that
         //  only ever runs the candidate section)
-        if constexpr (!NO_FLOW) if (st == LANE_RUN) {
+        if constexpr (!NO_FLOW) {
+        const int not_run0 = 32 - n_run;
+        const int thr = P.jump_thresh > 0 ? min(P.jump_thresh, (n_live + 1) >> 1) : 1;
+        for (;;) {
+        if (st == LANE_RUN) {
             const double hprop = tr.h;
             double step = hprop;
             bool clipped = false;
@@ -651,6 +657,10 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
                 }
                 tr.h = hnext;
             }
+        }
+        const int left = __popc(__ballot_sync(0xffffffffu, st != LANE_RUN)) - not_run0;   // lanes that landed (or failed)
+        if (n_wait + left >= thr || left == n_run) break;
+        }
         }
     }
 
