@@ -602,6 +602,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
         if constexpr (!NO_FLOW) {
         const int not_run0 = 32 - n_run;
         const int thr = P.jump_thresh > 0 ? min(P.jump_thresh, (n_live + 1) >> 1) : 1;
+        unsigned att = 0;
         for (;;) {
         if (st == LANE_RUN) {
             const double hprop = tr.h;
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
                 auto rhs = [&](const R* x, R* dx, R t) { tr.field(P, x, dx, t); };
                 e2 = rk_attempt<Tab, D, R>(rhs, tr.y, tr.k1, (R)tr.s, (R)step, yn, k7, (R)P.reltol, (R)P.abstol, inc);
             }
-            ++c_attempts;
+            ++att;
             const bool accept = e2 <= (R)D;
             double hnext;
             if (e2 < (sizeof(R) == 4 ? (R)3.4028234e38f : (R)1.7976931348623157e308)) {  // finite (false for NaN and Inf)
@@ -661,6 +662,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
         const int left = __popc(__ballot_sync(0xffffffffu, st != LANE_RUN)) - not_run0;   // lanes that landed (or failed)
         if (n_wait + left >= thr || left == n_run) break;
         }
+        c_attempts += att;
         }
     }
 
