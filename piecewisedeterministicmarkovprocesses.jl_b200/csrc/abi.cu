@@ -300,7 +300,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     P.n_jumps = o->n_jumps;
     P.max_attempts = o->max_attempts > 0 ? o->max_attempts : 1000000ll;
     P.save_pre = o->save_pre; P.save_post = o->save_post; P.tstop_policy = o->tstop_policy;
-    P.rng_mode = o->rng_mode; P.seed = o->seed; P.replay_stride = o->replay_stride;
+    P.rng_mode = o->rng_mode; P.seed = o->seed; P.keys = philox_round_keys(o->seed); P.replay_stride = o->replay_stride;
     {   // phase-scheduler thresholds (tunable for experiments)
         const char* ej = std::getenv("PDMP_JUMP_THRESH");
         const char* er = std::getenv("PDMP_REFILL_THRESH");
@@ -503,7 +503,7 @@ static int queue_chunk_d2h(pdmp_ensemble* e, int k, bool fetch_records) {
 static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool host_mode, bool fetch_records) {
     cudaStream_t s0 = user ? user : e->cs[0];
     e->last_stream = s0;
-    e->P.seed = seed;
+    e->P.seed = seed; e->P.keys = philox_round_keys(seed);
     e->host_mode_done = false;
     const int NC = e->m->info.n_c, ND = e->m->info.n_d;
     if (host_mode) {
@@ -780,7 +780,7 @@ static int solve_exact(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdm
     P.xc0_per_traj = d->xc0_per_traj; P.xd0_per_traj = d->xd0_per_traj;
     for (int i = 0; i < MAXP; ++i) P.parms[i] = i < d->n_parms ? d->parms[i] : 0.0;
     P.t0 = d->t0; P.tf = d->tf; P.n_jumps = o->n_jumps;
-    P.rng_mode = o->rng_mode; P.seed = o->seed; P.replay_stride = o->replay_stride;
+    P.rng_mode = o->rng_mode; P.seed = o->seed; P.keys = philox_round_keys(o->seed); P.replay_stride = o->replay_stride;
     const size_t nxc = (size_t)(d->xc0_per_traj ? n : 1) * N, nxd = (size_t)(d->xd0_per_traj ? n : 1) * N;
     for (size_t i = 0; i < nxd; ++i)
         if (d->xd0[i] > 0x3fffffffLL || d->xd0[i] < -0x3fffffffLL) return fail(PDMP_ERR_INVALID, "xd0 entries must fit in 31 bits");

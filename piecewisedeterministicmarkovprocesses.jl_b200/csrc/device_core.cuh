@@ -74,6 +74,26 @@ PDMP_DEV void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& 
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
+// the ten round keys (k0 + r W0, k1 + r W1) depend on the seed only: the host puts them in the kernel
+// parameters, so that they reach the XORs as constant-bank operands instead of ~40 uniform-datapath
+// instructions per call (Weyl increments + 32-bit immediates)
+struct PhiloxKeys { uint32_t k[10][2]; };
+inline PhiloxKeys philox_round_keys(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { K.k[r][0] = k0; K.k[r][1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return K;
+}
+PDMP_DEV void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, const PhiloxKeys& K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ K.k[r][0];
+        const uint32_t n2 = h0 ^ c3 ^ K.k[r][1];
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    }
+}
 PDMP_DEV double u01_from_bits(uint32_t hi, uint32_t lo) {
     const unsigned long long m = ((unsigned long long)hi << 20) | (lo >> 12);  // 52 bits
     return ((double)m + 0.5) * (1.0 / 4503599627370496.0);
@@ -85,7 +105,7 @@ struct DrawStream {
     PDMP_DEV void init() { idx = 0; cache = 0.0; }
     // REPLAY: reads the host-provided stream; PHILOX: draw k = block k/2, half k%2
     PDMP_DEV double next(int rng_mode, const double* __restrict__ replay, uint64_t replay_len, uint64_t gid,
-                         uint64_t seed, bool& exhausted) {
+                         const PhiloxKeys& keys, bool& exhausted) {
         const uint32_t k = idx++;
         if (rng_mode == 1) {
             if (k >= replay_len) { exhausted = true; return 0.5; }
@@ -93,7 +113,7 @@ struct DrawStream {
         }
         if (k & 1u) return cache;
         uint32_t c0 = (uint32_t)gid, c1 = (uint32_t)(gid >> 32), c2 = k >> 1, c3 = 0u;
-        philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+        philox4x32_10(c0, c1, c2, c3, keys);
         cache = u01_from_bits(c2, c3);
         return u01_from_bits(c0, c1);
     }
@@ -101,8 +121,8 @@ struct DrawStream {
     // next() calls): draws k, k+1 need block (k+1)/2 only — for even k both halves of it, for odd k the
     // cached half of the previous block and the first half of it.  Lanes whose idx parities differ
     // (Rejection: 2 or 3 draws per candidate) therefore stay converged through the Philox rounds.
-    PDMP_DEV void next2(int rng_mode, const double* __restrict__ replay, uint64_t replay_len, uint64_t gid, uint64_t seed,
-                        bool& exhausted, double& u0, double& u1) {
+    PDMP_DEV void next2(int rng_mode, const double* __restrict__ replay, uint64_t replay_len, uint64_t gid,
+                        const PhiloxKeys& keys, bool& exhausted, double& u0, double& u1) {
         const uint32_t k = idx;
         idx += 2;
         if (rng_mode == 1) {
@@ -111,7 +131,7 @@ struct DrawStream {
             return;
         }
         uint32_t c0 = (uint32_t)gid, c1 = (uint32_t)(gid >> 32), c2 = (k + 1u) >> 1, c3 = 0u;
-        philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+        philox4x32_10(c0, c1, c2, c3, keys);
         const double a = u01_from_bits(c0, c1), b = u01_from_bits(c2, c3);
         if (k & 1u) { u0 = cache; u1 = a; cache = b; }
         else { u0 = a; u1 = b; }

@@ -42,6 +42,7 @@ struct KParams {
     int save_pre, save_post, tstop_policy, rng_mode;
     int jump_thresh, refill_thresh;  // phase scheduler: lanes that must wait before JUMP / REFILL run
     unsigned long long seed;
+    PhiloxKeys keys;                 // round keys of `seed` (philox_round_keys)
     const double* replay_u;
     unsigned long long replay_stride;
     // sampling / statistics
@@ -86,6 +87,10 @@ template <class M> struct ConstRateOk<M, decltype((void)M::CONST_RATE_OK)> { sta
 template <class M, class = void> struct ChvSigned { static constexpr bool value = false; };
 template <class M> struct ChvSigned<M, decltype((void)M::CHV_SIGNED_SCALAR)> { static constexpr bool value = M::CHV_SIGNED_SCALAR; };
 
+// models whose F does not depend on (xc, t) between jumps (TCP: F = +-1): the plain-F flow is exact
+template <class M, class = void> struct ConstFlow { static constexpr bool value = false; };
+template <class M> struct ConstFlow<M, decltype((void)M::CONST_FLOW)> { static constexpr bool value = M::CONST_FLOW; };
+
 // geometric segment sizes: segment k holds REC_BLOCK << (k >> 2) records (4 segments per doubling)
 __host__ __device__ inline unsigned seg_records(int k) { return (unsigned)REC_BLOCK << (k >> 2); }
 
@@ -127,7 +132,7 @@ struct Traj {
     // ------------------------------------------------------------------------------
     PDMP_DEV double draw(const KParams& P, bool& exhausted) {
         return rng.next(P.rng_mode, P.replay_u + (size_t)lid * P.replay_stride, P.replay_stride,
-                        P.traj_id_offset + lid, P.seed, exhausted);
+                        P.traj_id_offset + lid, P.keys, exhausted);
     }
 
     // (chv::CHV)(xdot, x, caract, t): (F, 1) / Rtot      reference src/chvdiffeq.jl:6-16
@@ -232,6 +237,15 @@ struct Traj {
     PDMP_DEV bool flow_F(const KParams& P, R (&x)[NC], double& t, double tau, unsigned& aux_attempts, int& fail) {
         if constexpr (M::ZERO_FLOW) { t = tau; return true; }
         if (t == tau) return true;
+        if constexpr (ConstFlow<M>::value) {   // F is constant between jumps: the flow is x + F (tau - t), exactly
+            R f[NC];
+            M::F(f, x, xd, P.parms, (R)t);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) x[i] = fma(f[i], (R)(tau - t), x[i]);
+            t = tau;
+            ++aux_attempts;
+            return true;
+        }
         const double dir = tau > t ? 1.0 : -1.0;
         double hh = tau - t;
         PIController c2; c2.init();
@@ -445,7 +459,7 @@ struct Traj {
         const R bnd = M::bound(y, xd, P.parms, (R)tc);
         if (!(tot < bnd)) { finish(P, PDMP_ST_BOUND_VIOLATED); return true; }  // @assert :33
         double u_acc, u_exp;   // rand() of :35 then rand() of :36, one converged Philox call for both
-        rng.next2(P.rng_mode, P.replay_u + (size_t)lid * P.replay_stride, P.replay_stride, P.traj_id_offset + lid, P.seed,
+        rng.next2(P.rng_mode, P.replay_u + (size_t)lid * P.replay_stride, P.replay_stride, P.traj_id_offset + lid, P.keys,
                   ex, u_acc, u_exp);
         const bool reject = u_acc < 1.0 - (double)tot / (double)bnd;         // :35
         const double dtn = -log(u_exp) / (double)bnd;                        // :36

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ KPar
 
     auto draw = [&]() {
         return rng.next(P.rng_mode, P.replay_u + (size_t)idx * P.replay_stride, P.replay_stride,
-                        P.traj_id_offset + idx, P.seed, ex);
+                        P.traj_id_offset + idx, P.keys, ex);
     };
     auto save = [&](unsigned long long k) {          // _push_time! / push!(xc_hist) / push!(xd_hist), :87-89
         if (k >= O.cap) return;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ KPar
         else {
             double u_acc, u_exp;   // rand() of :67 then rand() of :69: one Philox call whatever the parity
             rng.next2(P.rng_mode, P.replay_u + (size_t)idx * P.replay_stride, P.replay_stride, P.traj_id_offset + idx,
-                      P.seed, ex, u_acc, u_exp);
+                      P.keys, ex, u_acc, u_exp);
             reject = u_acc < 1.0 - tot / bnd;
             dte = -log(u_exp);
         }

@@ -32,6 +32,7 @@ struct TcpDev {  // examples/tcp.jl:25-45
     static constexpr bool HAS_BOUND = true, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = true;
     static constexpr const char* NAME = "tcp";
     static constexpr int SCHED_JUMP = 16, SCHED_REFILL = 2;   // ~5.5 cheap RK attempts per jump
+    static constexpr bool CONST_FLOW = true;                  // F = +-1 between jumps: sample times and the last bit are exact
     template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
         dx[0] = (xd[0] & 1) ? R(-1) : R(1);  // mod(xd[1], 2) == 0 ? 1 : -1
     }
