@@ -95,8 +95,10 @@ PDMP_DEV void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& 
     }
 }
 PDMP_DEV double u01_from_bits(uint32_t hi, uint32_t lo) {
-    const unsigned long long m = ((unsigned long long)hi << 20) | (lo >> 12);  // 52 bits
-    return ((double)m + 0.5) * (1.0 / 4503599627370496.0);
+    // (m + 1/2) 2^-52 with the 52-bit integer m = hi:lo >> 12, built without an integer-to-double
+    // conversion: 1.m as a double in [1, 2), minus 1, plus 2^-53 — every step exact, the same value
+    const uint32_t mh = hi >> 12, ml = (hi << 20) | (lo >> 12);
+    return (__hiloint2double((int)(0x3ff00000u | mh), (int)ml) - 1.0) + 1.1102230246251565e-16;
 }
 
 struct DrawStream {
