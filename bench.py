@@ -60,7 +60,7 @@ def workload_config(n_traj, n_gpus):
                         "Int64 per trajectory on access): a saved point is 8 (t) + 8 (xc) + 2 x 2 (xd) = 20 B on the wire",
         "initial_conditions": "synthetic xc0_i = 0.5 + u_i (numpy PCG64 seed 2024), xd0 = [0, 1]",
         "rng": "philox4x32-10, seed = step index",
-        "l2": "working set (>= 40 GB of records per step) is far larger than the 126 MB L2; no flush needed",
+        "l2": "working set (42 GB of pool records + 26 GB of CSR per step) is far larger than the 126 MB L2; no flush needed",
         "parallelism": f"ensemble sharding x{n_gpus} (contiguous global id ranges), stats all-reduce only",
     }
 
@@ -265,7 +265,7 @@ def run_gpu(args):
     del fin
 
     # ---- end to end through the host-buffer API (H2D ICs, step, D2H of everything) ----
-    # the pinned host staging holds every record of a step (~51 GB at 10^7 trajectories): bound it
+    # the pinned host staging holds every record of a step (~27 GB at 10^7 trajectories): bound it
     # by the host memory actually available to this rank
     stats_t = hist_t = None
     ens.close()

@@ -518,7 +518,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
     CK(cudaMemsetAsync(e->d_ctl, 0, CTL_N * sizeof(unsigned long long), s0));
     if (e->n_stats) CK(cudaMemsetAsync(e->d_stats, 0, e->n_stats * sizeof(double), s0));
     if (e->n_hist) CK(cudaMemsetAsync(e->d_hist, 0, e->n_hist * sizeof(unsigned long long), s0));
-    // fork: both compute streams start after everything already ordered on s0
+    // fork: the compute streams start after everything already ordered on s0
     CK(cudaEventRecord(e->ev_fork, s0));
     for (auto st : e->cs) if (st != s0) CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
     CK(cudaEventRecord(e->ev_kbeg, e->cs[0]));
@@ -572,7 +572,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
         if (host_mode && k >= 1) { int rc = queue_chunk_d2h(e, k - 1, fetch_records); if (rc) return rc; }
     }
     if (host_mode && e->n) { int rc = queue_chunk_d2h(e, nch - 1, fetch_records); if (rc) return rc; }
-    // join: the caller's stream continues after both compute streams
+    // join: the caller's stream continues after the compute streams
     if (e->n) for (int k = std::max(0, nch - NS); k < nch; ++k) CK(cudaStreamWaitEvent(s0, e->ev_done[k], 0));
     e->ran = true;
     e->host_records = host_mode && fetch_records;

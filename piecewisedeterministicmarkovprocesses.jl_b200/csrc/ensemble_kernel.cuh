@@ -7,10 +7,11 @@
 //   init!      src/problem.jl:150-161      pfsample  src/utils.jl:46-57      affect!  src/jumps.jl:28-36
 //   saving     _push_time!/_push_xc!/_push_xd!  src/problem.jl:146-148
 //
-// Loop shape: every iteration each live lane performs exactly ONE adaptive RK attempt (so a
-// warp stays converged through the arithmetic-heavy part); lanes whose step landed on their
-// jump threshold then run the (short, divergent) jump section.  Lanes that finished their
-// trajectory pull the next one from the cursor with a warp-aggregated atomic.
+// Loop shape (phase scheduler, see the kernel): a warp alternates between three warp-uniform phases —
+// RK (an inner loop of adaptive step attempts for the running lanes, one ballot per attempt), JUMP
+// (the threshold section for all lanes that landed, preceded by a converged sampling pass) and
+// REFILL (finished lanes pull new trajectories from the global cursor with a warp-aggregated atomic).
+// The integrator state stays in registers throughout.
 #pragma once
 #include <algorithm>
 
