@@ -561,7 +561,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
             chunk_close_kernel<<<1, 32, 0, st>>>(e->d_nrec + a, e->d_offsets + a, b - a, Pk.blk_cursor, e->d_blkhist + k);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e->ev_base[k], st));
-            CK(e->m->compact(Pk, e->d_offsets + a, e->d_time, e->d_xc, e->d_xd, e->xb, st));
+            CK(e->m->compact(Pk, e->d_offsets + a, e->d_time, e->d_xc, e->d_xd, e->xb, nch > 1, st));
             CK(cudaMemcpyAsync(e->h_bound.p + k + 1, e->d_offsets + b, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         } else {
             chunk_close_kernel<<<1, 32, 0, st>>>(nullptr, nullptr, 0, Pk.blk_cursor, e->d_blkhist + k);

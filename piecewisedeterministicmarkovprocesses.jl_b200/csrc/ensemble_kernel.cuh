@@ -716,7 +716,7 @@ struct ModelEntry {
     cudaError_t (*occupancy)(int alg, int ode, int prec, bool records, bool stats, size_t smem, int* blocks_per_sm);
     // compaction pool -> CSR
     cudaError_t (*compact)(const KParams& P, const unsigned long long* offsets, double* time, double* xc,
-                           void* xd, int xd_bytes, cudaStream_t stream);
+                           void* xd, int xd_bytes, bool co_resident, cudaStream_t stream);
 };
 
 // pool -> CSR: one warp per trajectory walks its segments; reads are 16-byte vector loads of
@@ -724,12 +724,56 @@ struct ModelEntry {
 // Launch shape: 128 threads and at most 32 registers per thread, so that one compaction CTA
 // fits in the register space the resident ensemble CTAs leave free on every SM (e.g. TCP:
 // 6 x 128 x 80 = 61440 of 65536 registers) and the two kernels truly run concurrently.
+#ifndef PDMP_COMPACT_CTAS
+#define PDMP_COMPACT_CTAS 4
+#endif
+#ifndef PDMP_COMPACT_UNROLL
+#define PDMP_COMPACT_UNROLL 4
+#endif
+// one saved point: pool record -> the three CSR arrays
 template <class M, class XT>
-__global__ void __launch_bounds__(128, 16) compact_kernel(const KParams P, const unsigned long long* __restrict__ offsets,
-                                                      double* __restrict__ time, double* __restrict__ xc,
-                                                      XT* __restrict__ xd) {
-    using RL = RecLayout<M>;
+PDMP_DEV void csr_store(const double (&w)[RecLayout<M>::WORDS], unsigned long long o, double* __restrict__ time,
+                        double* __restrict__ xc, XT* __restrict__ xd) {
     constexpr int NC = M::NC, ND = M::ND;
+    __stcs(time + o, w[0]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) __stcs(xc + o * NC + c, w[1 + c]);
+    if constexpr (sizeof(XT) == 2 && ND % 2 == 0) {
+        // int16 transport: a pair of components is one 32-bit store
+        unsigned* dst = reinterpret_cast<unsigned*>(xd + o * ND);
+#pragma unroll
+        for (int c = 0; c < ND; c += 2) {
+            const double pw = w[1 + NC + c / 2];
+            __stcs(dst + c / 2, ((unsigned)__double2loint(pw) & 0xffffu) | ((unsigned)__double2hiint(pw) << 16));
+        }
+    } else if constexpr (sizeof(XT) == 4 && ND % 2 == 0) {
+        // int32 transport: the packed pool word is already the CSR layout
+        double* dst = reinterpret_cast<double*>(xd + o * ND);
+#pragma unroll
+        for (int c = 0; c < ND; c += 2) __stcs(dst + c / 2, w[1 + NC + c / 2]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < ND; ++c) {
+            const double pw = w[1 + NC + c / 2];
+            const int v = (c & 1) ? __double2hiint(pw) : __double2loint(pw);
+            xd[o * ND + c] = (XT)v;
+        }
+    }
+}
+
+// CO = true: the variant that shares the SMs with a running ensemble kernel (host-mode pipeline):
+// 128 threads, <= 32 registers, one group of 32 records in flight per warp.  CO = false: the
+// stand-alone variant of resident runs: four groups of 32 records in flight per warp (the kernel is
+// bound by dependent-load latency, not by instructions) and only 4 CTAs per SM — fewer concurrent
+// streams keep DRAM pages open.  Measured pool -> CSR times (TCP 4 M / SIR 2 M / Morris-Lecar 1 M
+// trajectories): co-resident shape 7.0 / 9.5 / 16.0 ms; unroll 2 x 8 CTAs 6.7 / 7.0 / 12.8;
+// unroll 4 x 4 CTAs 6.7 / 6.2 / 10.0; unroll 4 x 12 CTAs is worse than 8.
+template <class M, class XT, bool CO>
+__global__ void __launch_bounds__(128, CO ? 16 : PDMP_COMPACT_CTAS) compact_kernel(const KParams P, const unsigned long long* __restrict__ offsets,
+                                                               double* __restrict__ time, double* __restrict__ xc,
+                                                               XT* __restrict__ xd) {
+    using RL = RecLayout<M>;
+    constexpr int UN = CO ? 1 : PDMP_COMPACT_UNROLL;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -740,43 +784,29 @@ __global__ void __launch_bounds__(128, 16) compact_kernel(const KParams P, const
         // record r lives in segment k = 4m + q / (16 << m) at position q % (16 << m), where
         // m = floor(log2(r / 64 + 1)) is the size level and q = r - 64 (2^m - 1): every warp
         // iteration moves 32 consecutive records whatever the segment boundaries
-        for (unsigned r = lane; r < n; r += 32) {
-            const unsigned m = 31u - __clz((r >> 6) + 1u);
-            const unsigned q = r - (64u << m) + 64u;
-            const unsigned k = 4u * m + (q >> (4u + m));
-            const unsigned pos = q & ((16u << m) - 1u);
-            const unsigned long long slot = (unsigned long long)__ldg(tab + k) * REC_BLOCK + pos;
-            const double2* src = reinterpret_cast<const double2*>(P.pool + slot * RL::BYTES);
-            double w[RL::WORDS];
+        for (unsigned r0 = lane; r0 < n; r0 += 32 * UN) {
+            double w[UN][RL::WORDS];
 #pragma unroll
-            for (int j = 0; j < RL::WORDS / 2; ++j) {
-                const double2 v = __ldcs(src + j);
-                w[2 * j] = v.x; w[2 * j + 1] = v.y;
+            for (int u = 0; u < UN; ++u) {
+                const unsigned r = r0 + 32 * u;
+                if (r < n) {
+                    const unsigned m = 31u - __clz((r >> 6) + 1u);
+                    const unsigned q = r - (64u << m) + 64u;
+                    const unsigned k = 4u * m + (q >> (4u + m));
+                    const unsigned pos = q & ((16u << m) - 1u);
+                    const unsigned long long slot = (unsigned long long)__ldg(tab + k) * REC_BLOCK + pos;
+                    const double2* src = reinterpret_cast<const double2*>(P.pool + slot * RL::BYTES);
+#pragma unroll
+                    for (int j = 0; j < RL::WORDS / 2; ++j) {
+                        const double2 v = __ldcs(src + j);
+                        w[u][2 * j] = v.x; w[u][2 * j + 1] = v.y;
+                    }
+                }
             }
-            const unsigned long long o = off + r;
-            __stcs(time + o, w[0]);
 #pragma unroll
-            for (int c = 0; c < NC; ++c) __stcs(xc + o * NC + c, w[1 + c]);
-            if constexpr (sizeof(XT) == 2 && ND % 2 == 0) {
-                // int16 transport: a pair of components is one 32-bit store
-                unsigned* dst = reinterpret_cast<unsigned*>(xd + o * ND);
-#pragma unroll
-                for (int c = 0; c < ND; c += 2) {
-                    const double pw = w[1 + NC + c / 2];
-                    __stcs(dst + c / 2, ((unsigned)__double2loint(pw) & 0xffffu) | ((unsigned)__double2hiint(pw) << 16));
-                }
-            } else if constexpr (sizeof(XT) == 4 && ND % 2 == 0) {
-                // int32 transport: the packed pool word is already the CSR layout
-                double* dst = reinterpret_cast<double*>(xd + o * ND);
-#pragma unroll
-                for (int c = 0; c < ND; c += 2) __stcs(dst + c / 2, w[1 + NC + c / 2]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < ND; ++c) {
-                    const double pw = w[1 + NC + c / 2];
-                    const int v = (c & 1) ? __double2hiint(pw) : __double2loint(pw);
-                    xd[o * ND + c] = (XT)v;
-                }
+            for (int u = 0; u < UN; ++u) {
+                const unsigned r = r0 + 32 * u;
+                if (r < n) csr_store<M, XT>(w[u], off + r, time, xc, xd);
             }
         }
     }
@@ -828,18 +858,24 @@ cudaError_t model_occupancy(int alg, int ode, int prec, bool records, bool stats
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kern, BLOCK, smem);
     });
 }
+template <class M, class XT>
+cudaError_t compact_launch(bool co_resident, const KParams& P, const unsigned long long* offsets, double* time, double* xc,
+                           XT* xd, int sms, cudaStream_t st) {
+    const unsigned long long want = (P.n_traj + 3) / 4;  // 4 warps per CTA, one trajectory per warp at a time
+    const int grid = (int)std::min<unsigned long long>(want ? want : 1, (unsigned long long)sms * (co_resident ? 16 : PDMP_COMPACT_CTAS));
+    if (co_resident) compact_kernel<M, XT, true><<<grid, 128, 0, st>>>(P, offsets, time, xc, xd);
+    else compact_kernel<M, XT, false><<<grid, 128, 0, st>>>(P, offsets, time, xc, xd);
+    return cudaGetLastError();
+}
 template <class M>
 cudaError_t model_compact(const KParams& P, const unsigned long long* offsets, double* time, double* xc,
-                          void* xd, int xd_bytes, cudaStream_t st) {
+                          void* xd, int xd_bytes, bool co_resident, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    unsigned long long want = (P.n_traj + 3) / 4;  // 4 warps per CTA, one trajectory per warp at a time
-    const int grid = (int)std::min<unsigned long long>(want ? want : 1, (unsigned long long)sms * 16);
-    if (xd_bytes == 2) compact_kernel<M, short><<<grid, 128, 0, st>>>(P, offsets, time, xc, (short*)xd);
-    else if (xd_bytes == 4) compact_kernel<M, int><<<grid, 128, 0, st>>>(P, offsets, time, xc, (int*)xd);
-    else compact_kernel<M, long long><<<grid, 128, 0, st>>>(P, offsets, time, xc, (long long*)xd);
-    return cudaGetLastError();
+    if (xd_bytes == 2) return compact_launch<M, short>(co_resident, P, offsets, time, xc, (short*)xd, sms, st);
+    if (xd_bytes == 4) return compact_launch<M, int>(co_resident, P, offsets, time, xc, (int*)xd, sms, st);
+    return compact_launch<M, long long>(co_resident, P, offsets, time, xc, (long long*)xd, sms, st);
 }
 
 template <class M>
