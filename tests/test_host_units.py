@@ -100,3 +100,46 @@ def test_result_views(orc, P):
     d = np.diff(tr.xd, axis=1).T
     allowed = {(-1, 1, 0, 0), (1, -1, 0, 1), (0, 0, -1, 1), (0, 0, 1, -1)}
     assert {tuple(x) for x in d} <= allowed
+
+
+def test_marshal_transport_rate_kind_and_save_counts(P):
+    """Host-side decisions that never reach a GPU: the narrow xd transport is chosen only when it is
+    provably exact, rate wrappers map to rate_kind, exact-flow options are forwarded."""
+    import ctypes as C
+    from pdmp_b200 import _marshal, _abi
+
+    def info(n_c, n_d, n_r, n_parms=1, has_delta=0, name=b"m"):
+        i = _abi.ModelInfo()
+        i.n_c, i.n_d, i.n_r, i.n_parms, i.has_delta, i.name = n_c, n_d, n_r, n_parms, has_delta, name
+        return i
+
+    pb = P.models.problem("tcp", tspan=(0.0, 200.0))
+    kw = dict(algorithm="chv", trajectories=4)
+    _, o, _ = _marshal.build(pb, info(1, 2, 2), n_jumps=1000, **kw)
+    assert o.xd_bytes == 8                                           # default: the reference's Int64 layout
+    _, o, _ = _marshal.build(pb, info(1, 2, 2), n_jumps=1000, xd_transport="auto", **kw)
+    assert o.xd_bytes == 2                                           # |xd| <= 1 + 999
+    _, o, _ = _marshal.build(pb, info(1, 2, 2), n_jumps=40000, xd_transport="auto", **kw)
+    assert o.xd_bytes == 4                                           # 40000 jumps could overflow int16
+    _, o, _ = _marshal.build(pb, info(1, 2, 2, has_delta=1), n_jumps=10, xd_transport="auto", **kw)
+    assert o.xd_bytes == 4                                           # a Delta may move xd arbitrarily
+    with pytest.raises(ValueError):
+        _marshal.build(pb, info(1, 2, 2), n_jumps=40000, xd_transport="int16", **kw)
+    ex = P.models.EXAMPLES["tcp"]
+    for wrap, kind in ((P.VariableRate, 0), (P.ConstantRate, 1)):
+        q = P.PDMPProblem("tcp", wrap("tcp"), np.array(ex["nu"]), ex["xc0"], ex["xd0"], ex["parms"], (0.0, 1.0))
+        d, _, _ = _marshal.build(q, info(1, 2, 2), n_jumps=5, **kw)
+        assert d.rate_kind == kind
+    q = P.PDMPProblem("tcp", P.CompositeRate("tcp", "tcp"), np.array(ex["nu"]), ex["xc0"], ex["xd0"], ex["parms"], (0.0, 1.0))
+    with pytest.raises(NotImplementedError):
+        _marshal.build(q, info(1, 2, 2), n_jumps=5, **kw)
+    mf = P.models.problem("neuron_mf")
+    d, o, _ = _marshal.build(mf, info(100, 100, 100), algorithm="rejection_exact", trajectories=2, n_jumps=50,
+                             save_c_count=2, save_d_count=3)
+    assert (o.algorithm, o.save_c_count, o.save_d_count) == (_abi.ALG_REJECTION_EXACT, 2, 3)
+    assert isinstance(P.RejectionExactGPU("neuron_mf"), P.AbstractRejection)
+    # per-trajectory initial conditions and the shape check against the device functor
+    d, _, keep = _marshal.build(pb, info(1, 2, 2), n_jumps=5, algorithm="chv", trajectories=3, xc0=np.ones((3, 1)))
+    assert d.xc0_per_traj == 1 and d.xd0_per_traj == 0 and d.n_traj == 3
+    with pytest.raises(ValueError):
+        _marshal.build(pb, info(2, 2, 2), n_jumps=5, **kw)
