@@ -725,10 +725,10 @@ struct ModelEntry {
 // fits in the register space the resident ensemble CTAs leave free on every SM (e.g. TCP:
 // 6 x 128 x 80 = 61440 of 65536 registers) and the two kernels truly run concurrently.
 #ifndef PDMP_COMPACT_CTAS
-#define PDMP_COMPACT_CTAS 4
+#define PDMP_COMPACT_CTAS 8
 #endif
 #ifndef PDMP_COMPACT_UNROLL
-#define PDMP_COMPACT_UNROLL 4
+#define PDMP_COMPACT_UNROLL 2
 #endif
 // one saved point: pool record -> the three CSR arrays
 template <class M, class XT>
@@ -763,11 +763,12 @@ PDMP_DEV void csr_store(const double (&w)[RecLayout<M>::WORDS], unsigned long lo
 
 // CO = true: the variant that shares the SMs with a running ensemble kernel (host-mode pipeline):
 // 128 threads, <= 32 registers, one group of 32 records in flight per warp.  CO = false: the
-// stand-alone variant of resident runs: four groups of 32 records in flight per warp (the kernel is
-// bound by dependent-load latency, not by instructions) and only 4 CTAs per SM — fewer concurrent
-// streams keep DRAM pages open.  Measured pool -> CSR times (TCP 4 M / SIR 2 M / Morris-Lecar 1 M
-// trajectories): co-resident shape 7.0 / 9.5 / 16.0 ms; unroll 2 x 8 CTAs 6.7 / 7.0 / 12.8;
-// unroll 4 x 4 CTAs 6.7 / 6.2 / 10.0; unroll 4 x 12 CTAs is worse than 8.
+// stand-alone variant of resident runs: two groups of 32 records in flight per warp (the kernel is
+// bound by dependent-load latency, not by instructions), 8 CTAs per SM.  Measured pool -> CSR times
+// (TCP 4 M / SIR 2 M / Morris-Lecar 1 M trajectories): co-resident shape 7.0 / 9.5 / 16.0 ms; unroll
+// 2 x 8 CTAs 6.7 / 7.0 / 12.8; unroll 4 x 4 CTAs 6.7 / 6.2 / 10.0 — but the latter loses at the
+// bench size (10^7 TCP trajectories, mostly short: 18.5 ms against 16.3 for 2 x 8 and 16.6 for the
+// co-resident shape), where many warps in flight matter more than open DRAM pages.
 template <class M, class XT, bool CO>
 __global__ void __launch_bounds__(128, CO ? 16 : PDMP_COMPACT_CTAS) compact_kernel(const KParams P, const unsigned long long* __restrict__ offsets,
                                                                double* __restrict__ time, double* __restrict__ xc,
