@@ -44,8 +44,8 @@ FLOPS_PER_ATTEMPT_TCP = 180.0   # D*72 + 2 + 10 + 6*C_rhs, D =
 REC_BYTES_TCP = 32.0            # 8*(1+n_c) + 8*n_d per saved point; pool record
 CSR_BYTES_TCP = 20.0            # CSR / wire record with int16 xd transport: 8 + 8 + 2*2
 # DRAM bytes per saved record measured by `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum over the
-# records of that launch; profiles/r1_tcp_kernel_v9_full.txt, profiles/r1_compact_kernel_v9_full.txt)
-NCU_DRAM_BYTES_PER_RECORD = {"ensemble_kernel": 33.1, "compact_kernel": 54.2}
+# records of that launch; profiles/r1_tcp_kernel_v11_full.txt, profiles/r1_compact_kernel_v11_full.txt)
+NCU_DRAM_BYTES_PER_RECORD = {"ensemble_kernel": 33.1, "compact_kernel": 53.4}
 
 
 def workload_config(n_traj, n_gpus):
