@@ -272,6 +272,10 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
         error("problem shape does not match device model $(algo.model)")
     (algo isa RejectionExactGPU) == (info.exact_flow != 0) ||
         error("RejectionExactGPU needs an exact-flow device model (and only it can run one)")
+    if xd_bytes == 2   # int16 transport must be provably exact: |xd0| + (n_jumps - 1) max|nu|, and no Delta on xd
+        bound = maximum(abs, car.xd0; init = 0) + max(Int64(n_jumps) - 1, 0) * maximum(abs, nu; init = 0)
+        (bound < 32768 && info.has_delta == 0) || error("xd_bytes = 2 is not provably exact for this problem (bound $bound)")
+    end
     xc = xc0 === nothing ? Vector{Float64}(car.xc0) : Matrix{Float64}(xc0)
     xd = xd0 === nothing ? Vector{Int64}(car.xd0) : Matrix{Int64}(xd0)
     parms = car.parms isa AbstractVector ? Vector{Float64}(car.parms) : Float64[]
