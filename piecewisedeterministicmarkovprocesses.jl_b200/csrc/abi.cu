@@ -773,8 +773,12 @@ static int solve_exact(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdm
     e->device = o->device; e->o = *o; e->n = n;
     for (auto& st : e->cs) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     cudaStream_t st = e->cs[0];
-    cudaEvent_t ev[4];
-    for (auto& v : ev) CK(cudaEventCreate(&v));
+    struct Events {   // destroyed on every exit path
+        cudaEvent_t v[4] = {};
+        ~Events() { for (auto x : v) if (x) cudaEventDestroy(x); }
+    } evs;
+    cudaEvent_t* ev = evs.v;
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&ev[i]));
     KParams& P = e->P;
     P.n_traj = n; P.traj_id_offset = d->traj_id_offset;
     P.xc0_per_traj = d->xc0_per_traj; P.xd0_per_traj = d->xd0_per_traj;
@@ -858,7 +862,6 @@ static int solve_exact(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdm
     CK(cudaStreamSynchronize(st));
     float kms = 0, cms = 0;
     CK(cudaEventElapsedTime(&kms, ev[0], ev[1])); CK(cudaEventElapsedTime(&cms, ev[2], ev[3]));
-    for (auto& v : ev) cudaEventDestroy(v);
     std::memset(r, 0, sizeof(*r));
     r->n_traj = n; r->total_records = total; r->records_needed = total;
     r->offsets = (uint64_t*)e->h_offsets.p; r->time = e->h_time.p; r->xc = e->h_xc.p; r->xd = e->h_xd.p;
