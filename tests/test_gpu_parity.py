@@ -628,3 +628,20 @@ def test_rejection_exact_parity(G, orc):
         G.solve(pb, G.RejectionGPU("neuron_mf"), trajectories=2, n_jumps=10)
     with pytest.raises(G.PDMPError):
         G.solve(G.models.problem("tcp"), G.RejectionExactGPU("tcp"), trajectories=2, n_jumps=10)
+
+
+@pytest.mark.parametrize("model,tf,nj", [("tcp", 200.0, 60), ("tcp2d", 10.0, 200), ("pdmp_stiff", 1e5, 40)])
+def test_replay_parity_with_tstop_policy_1(G, orc, model, tf, nj):
+    # the bench's step-size policy after a clipped step (tstop_policy): same parity bar
+    pb = G.models.problem(model)
+    pb.tspan[1] = tf
+    U = uniforms(77, 500, 2 * nj + 8)
+    kw = dict(trajectories=500, n_jumps=nj, replay=U, reltol=1e-10, abstol=1e-13, tstop_policy=1)
+    g = G.solve(pb, G.CHVGPU(model), **kw)
+    c = orc.solve(pb, model, algorithm="chv", ode="dp5", **kw)
+    same_discrete(g, c)
+    assert relerr(g.time, c.time) < 1e-8 and relerr(g.xc, c.xc) < 1e-8
+    # and it does save attempts at the reference's default tolerances
+    a0 = G.solve(pb, G.CHVGPU(model), trajectories=500, n_jumps=nj, replay=U).counters["rk_attempts"]
+    a1 = G.solve(pb, G.CHVGPU(model), trajectories=500, n_jumps=nj, replay=U, tstop_policy=1).counters["rk_attempts"]
+    assert a1 <= a0
