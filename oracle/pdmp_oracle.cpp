@@ -481,6 +481,14 @@ struct Stats {
     }
 };
 
+// RK attempt budget per trajectory (OrdinaryDiffEq maxiters): opts.max_attempts, or by default
+// max(10^6, 64 n_jumps) so that long runs are not cut short (same rule as the CUDA library)
+inline uint64_t default_max_attempts(const pdmp_solve_opts& o) {
+    if (o.max_attempts > 0) return (uint64_t)o.max_attempts;
+    const uint64_t scaled = o.n_jumps > 0 ? 64ull * (uint64_t)std::min<int64_t>(o.n_jumps, (int64_t)1 << 40) : 0;
+    return std::min<uint64_t>(std::max<uint64_t>(1000000ull, scaled), 0x7fffffffull);
+}
+
 template <class M>
 struct Sampler {
     // plain-F flow used for sample times and the "last bit" (reference src/chvdiffeq.jl:160-168):
@@ -562,7 +570,7 @@ void chv_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut& out,
     const double ti = d.t0, tf = d.tf;
     const double* p = d.parms;
     const Tableau* tab = o.ode == PDMP_ODE_TSIT5 ? &TSIT5 : &DP5;
-    const uint64_t max_attempts = o.max_attempts > 0 ? (uint64_t)o.max_attempts : 1000000ull;
+    const uint64_t max_attempts = default_max_attempts(o);
 
     // init!(problem), src/problem.jl:150-161 and :95-99
     double xc[NC];      // caract.xc: post-jump continuous state
@@ -614,13 +622,15 @@ void chv_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut& out,
         {
             double rr[2];
             M::R(rate, it.u, xd, p, tj, false, rr);  // :51, rates at the PRE-jump state
+        }
+        if (tj < tf) {                                  // :52
             // docs/src/solver.md:41-42 requires a positive total rate; the reference would
-            // sample from an all-zero / NaN vector here, we flag the trajectory instead
+            // sample from an all-zero / NaN vector here, we flag the trajectory instead.  Only where
+            // pfsample uses the rates: at the overshoot threshold (tj >= tf) the reference computes
+            // them and ignores them, then does the last bit and returns normally.
             double tot = rate[0];
             for (int k = 1; k < NR; ++k) tot += rate[k];
             if (!(tot > 0.0) || !std::isfinite(tot)) { out.status = PDMP_ST_NONPOSITIVE_RATE; break; }
-        }
-        if (tj < tf) {                                  // :52
             const int ev = pfsample(rate, NR, rng.next());  // :57
             for (int k = 0; k < ND; ++k) xd[k] += sh.nu[ev - 1][k];  // affect!, src/jumps.jl:28-36
             M::Delta(it.u, xd, p, tj, ev);
@@ -675,7 +685,7 @@ void rejection_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut
     const double ti = d.t0, tf = d.tf;
     const double* p = d.parms;
     const Tableau* tab = o.ode == PDMP_ODE_TSIT5 ? &TSIT5 : &DP5;
-    const uint64_t max_attempts = o.max_attempts > 0 ? (uint64_t)o.max_attempts : 1000000ull;
+    const uint64_t max_attempts = default_max_attempts(o);
 
     double xc[NC];  // caract.xc: state at the last ACCEPTED jump
     int64_t xd[ND];

@@ -63,17 +63,28 @@ static unsigned long long max_records_per_traj(const pdmp_solve_opts& o) {
     const unsigned long long thr = (unsigned long long)std::max<long long>(o.n_jumps - 1, 0);
     return 2ull + thr * (unsigned long long)((o.save_pre ? 1 : 0) + (o.save_post ? 1 : 0));
 }
+// the writer's per-trajectory cursors are 32-bit and segment k holds 16 << (k >> 2) records: a
+// trajectory may store at most 2^30 records (create() rejects larger n_jumps with PDMP_ERR_INVALID)
+constexpr unsigned long long MAX_RECORDS_PER_TRAJ = 1ull << 30;
 static int table_width(unsigned long long maxrec) {
     unsigned long long cap = 0;
     int k = 0;
-    while (cap < maxrec) { cap += seg_records(k); ++k; }
+    while (cap < maxrec && k < 124) { cap += (unsigned long long)REC_BLOCK << (k >> 2); ++k; }
     return std::max(k, 1);
 }
 static unsigned long long pool_records_for(unsigned long long nrec) {  // capacity a trajectory of nrec records uses
     unsigned long long cap = 0;
     int k = 0;
-    while (cap < nrec) { cap += seg_records(k); ++k; }
+    while (cap < nrec && k < 124) { cap += (unsigned long long)REC_BLOCK << (k >> 2); ++k; }
     return cap;
+}
+// RK attempt budget per trajectory (OrdinaryDiffEq's maxiters): opts.max_attempts, or by default
+// max(10^6, 64 n_jumps) — about ten times the attempts a run of n_jumps jumps needs — so that long
+// runs are not cut short; the budget covers the main integrator, sub-integrations have their own
+static long long default_max_attempts(const pdmp_solve_opts& o) {
+    if (o.max_attempts > 0) return o.max_attempts;
+    const long long scaled = 64ll * std::min<long long>(o.n_jumps, 1ll << 40);
+    return std::min<long long>(std::max<long long>(1000000ll, scaled), 0x7fffffffll);
 }
 
 template <class T>
@@ -228,6 +239,9 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         return fail(PDMP_ERR_MODEL, std::string("model '") + m.info.name + "' has no exact flow: use CHV or Rejection");
     const int NC = m.info.n_c, ND = m.info.n_d, NR = m.info.n_r;
     if (o->n_jumps < 1) return fail(PDMP_ERR_INVALID, "n_jumps must be >= 1 and finite");
+    if (!o->no_records && max_records_per_traj(*o) > MAX_RECORDS_PER_TRAJ)
+        return fail(PDMP_ERR_INVALID, "n_jumps: a trajectory may save at most 2^30 points; lower n_jumps, or run with "
+                                      "no_records / save_positions = (false, false)");
     if (!(d->t0 < d->tf)) return fail(PDMP_ERR_INVALID, "tspan must satisfy t0 < tf");
     if (!(o->reltol > 0) || !(o->abstol >= 1e-300)) return fail(PDMP_ERR_INVALID, "reltol must be > 0 and abstol >= 1e-300");
     if (d->n_parms < m.info.n_parms || d->n_parms > MAXP)
@@ -298,7 +312,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     P.rate_const = d->rate_kind == 1;
     P.reltol = o->reltol; P.abstol = o->abstol;
     P.n_jumps = o->n_jumps;
-    P.max_attempts = o->max_attempts > 0 ? o->max_attempts : 1000000ll;
+    P.max_attempts = default_max_attempts(*o);
     P.save_pre = o->save_pre; P.save_post = o->save_post; P.tstop_policy = o->tstop_policy;
     P.rng_mode = o->rng_mode; P.seed = o->seed; P.keys = philox_round_keys(o->seed); P.replay_stride = o->replay_stride;
     {   // phase-scheduler thresholds (tunable for experiments)
@@ -394,15 +408,16 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         if (e->shared_pool) {
             npools = 1;
             pool_rec = want;
-            e->csr_cap = want;
         } else {
             pool_rec = (unsigned long long)std::ceil((double)want * chunk_frac * 1.06);
             pool_rec = std::max<unsigned long long>(pool_rec, e->chunk_n * REC_BLOCK);
             pool_rec = std::min<unsigned long long>(pool_rec, e->chunk_n * per_traj_worst);
         }
         e->pool_blocks = (pool_rec + REC_BLOCK - 1) / REC_BLOCK;
-        // the CSR must hold whatever the pools can hold (a chunk never stores more than its pool)
-        if (!e->shared_pool)
+        // the CSR must hold whatever the pools can hold (a chunk never stores more than its pool): the pool is
+        // handed out in whole blocks, so a shared pool stores up to pool_blocks * REC_BLOCK >= want records
+        if (e->shared_pool) e->csr_cap = e->pool_blocks * REC_BLOCK;
+        else
             e->csr_cap = std::min<unsigned long long>(worst, e->pool_blocks * REC_BLOCK * (unsigned long long)e->n_chunks);
         const size_t pool_bytes = (size_t)e->pool_blocks * REC_BLOCK * rec_bytes;
         if (pool_bytes * npools + e->csr_cap * csr_bytes + fixed > free_b)

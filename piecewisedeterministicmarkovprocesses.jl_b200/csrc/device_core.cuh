@@ -58,6 +58,20 @@ PDMP_DEV float rcp_weight(float x) {
     return r;
 }
 
+// max(|a|, |b|) of the error weights as compare + select.  fmax's NaN rules are not needed here (a NaN
+// stage makes the error estimate NaN whichever operand is picked, and the caller treats that as a
+// failed trial step); for finite operands the value is the one fmax returns.
+template <class R> PDMP_DEV R max_abs(R a, R b) {
+    return fabs(fabs(a) > fabs(b) ? a : b);   // select the raw operand: |.| folds into the consumer as an operand modifier
+}
+// h with the sign of component i of a sign vector given as a bit mask (bit i set: c_i = -1)
+PDMP_DEV double apply_sign(double h, unsigned negmask, int i) {
+    return __hiloint2double(__double2hiint(h) ^ (int)(((negmask >> i) & 1u) << 31), __double2loint(h));
+}
+PDMP_DEV float apply_sign(float h, unsigned negmask, int i) {
+    return __int_as_float(__float_as_int(h) ^ (int)(((negmask >> i) & 1u) << 31));
+}
+
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  counter = (gid_lo, gid_hi, block, 0),
 // key = (seed_lo, seed_hi).  One call yields two 52-bit uniforms in (0,1): exactly one
@@ -294,7 +308,7 @@ PDMP_DEV R rk_attempt(RHS&& f, const R (&u)[D], const R (&k1)[D], R t, R h, R (&
 #pragma unroll
         for (int j = 1; j < 7; ++j)
             if (Tab::bt(j) != 0.0) acc = fma(Tab::template BT<R>(j), k[j][i], acc);
-        const R sc = fma(fmax(fabs(u[i]), fabs(unew[i])), reltol, abstol);
+        const R sc = fma(max_abs(u[i], unew[i]), reltol, abstol);
         const R r = (h * acc) * rcp_weight(sc);
         e2 = fma(r, r, e2);
         k7[i] = k[6][i];
@@ -307,13 +321,14 @@ PDMP_DEV R rk_attempt(RHS&& f, const R (&u)[D], const R (&k1)[D], R t, R h, R (&
 // serves all components (k_j[i] = c_i g_j exactly, hence sum_j a_sj k_j[i] = c_i sum_j a_sj g_j bit for
 // bit: the results are identical to rk_attempt, with about half the FMAs and a third of the stage
 // registers).  TCP in CHV variables is such a field: (F, 1) / Rtot = (+-1, 1) * x.
+// The sign vector arrives as a bit mask (bit i set: c_i = -1) and is applied to h by flipping its sign bit.
 template <class Tab, int D, class R, class G>
-PDMP_DEV R rk_attempt_signed(G&& g, const R (&c)[D], const R (&u)[D], R g1, R t, R h, R (&unew)[D], R& g7, R reltol,
+PDMP_DEV R rk_attempt_signed(G&& g, unsigned negmask, const R (&u)[D], R g1, R t, R h, R (&unew)[D], R& g7, R reltol,
                              R abstol, R& inc_last) {
     R gk[7], hc[D];
     gk[0] = g1;
 #pragma unroll
-    for (int i = 0; i < D; ++i) hc[i] = h * c[i];
+    for (int i = 0; i < D; ++i) hc[i] = apply_sign(h, negmask, i);
 #pragma unroll
     for (int s = 1; s < 7; ++s) {
         R acc = Tab::template A<R>(s - 1, 0) * gk[0];
@@ -338,7 +353,7 @@ PDMP_DEV R rk_attempt_signed(G&& g, const R (&c)[D], const R (&u)[D], R g1, R t,
     R e2 = R(0);
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-        const R sc = fma(fmax(fabs(u[i]), fabs(unew[i])), reltol, abstol);
+        const R sc = fma(max_abs(u[i], unew[i]), reltol, abstol);
         const R r = he * rcp_weight(sc);
         e2 = fma(r, r, e2);
     }
@@ -365,6 +380,19 @@ struct PIController {
     // returns the factor f such that h_next = h * f
     //   accept : f = 1/q,  q = clamp(EEst^b1 / qold^b2 / gamma, 1/qmax, 1/qmin)
     //   reject : f = 1/min(1/qmin, EEst^b1 / gamma)
+    // The same two formulas on e2 = D EEst^2 straight from the attempt (log2 D is subtracted in the log
+    // domain), as separate entry points: accepted steps are the hot path, rejections are rare.
+    template <int D> PDMP_DEV float accept(float e2) {
+        const float l = lg2_approx(e2) - (D == 1 ? 0.0f : D == 2 ? 1.0f : D == 3 ? 1.58496250072f : D == 4 ? 2.0f : __log2f((float)D));
+        float lq = 0.07f * l - 0.04f * lq2 + 0.15200309344f;
+        lq = fminf(fmaxf(lq, -3.32192809489f), 2.32192809489f);
+        lq2 = fmaxf(l, -26.575424759f);
+        return ex2_approx(-lq);
+    }
+    template <int D> PDMP_DEV float reject(float e2) const {
+        const float l = lg2_approx(e2) - (D == 1 ? 0.0f : D == 2 ? 1.0f : D == 3 ? 1.58496250072f : D == 4 ? 2.0f : __log2f((float)D));
+        return ex2_approx(-fminf(0.07f * l + 0.15200309344f, 2.32192809489f));
+    }
     PDMP_DEV float step(float EEst2, bool accept) {
         const float l = lg2_approx(EEst2);            // log2(EEst^2); -inf for EEst = 0
         const float lq11 = 0.07f * l;                        // log2(EEst^beta1), beta1 = 7/50

@@ -111,7 +111,9 @@ struct Traj {
     R k1[D];            // FSAL
     double tacc;        // SHADOW_T only: the time slot in double
     R inv_rate;         // ConstantRate (src/rate.jl:17-40): 1 / total rate, cached from jump to jump
-    double s, tstop, h; // integration variable, next threshold, proposed step
+    double r, tstop, h; // distance of the integration variable to the next threshold (s = tstop - r; an
+                        // accepted step subtracts from it, a landing makes it exactly 0), the threshold, the
+                        // proposed step.  The CHV field is autonomous in s, so s itself is never formed there.
     PIController pi;
     // ---- PDMP state ----
     int xd[ND];
@@ -203,10 +205,12 @@ struct Traj {
         if constexpr (!STATS) return;
         const int C = P.n_comp, TC = P.n_sample * C;
         if (P.stats_in_smem) {
+            // the count is the same for every component: ONE native 32-bit shared atomic per sample (64-bit
+            // shared atomics are CAS loops); the slot of component 0 holds it as an integer until the flush
+            atomicAdd(reinterpret_cast<unsigned*>(sstat + j * C), 1u);
 #pragma unroll
             for (int c = 0; c < NC + ND; ++c) {
                 const double v = c < NC ? (double)xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
-                atomicAdd(sstat + j * C + c, 1.0);
                 atomicAdd(sstat + TC + j * C + c, v);
                 atomicAdd(sstat + 2 * TC + j * C + c, v * v);
             }
@@ -295,10 +299,11 @@ struct Traj {
     // so the sample lies within the step just taken: it is reached by flowing plain F BACKWARDS
     // from the current state (typically one RK attempt), and the current xd is the state there.
     // time the trajectory has reached (CHV: the time slot; Rejection: s is time)
+    PDMP_DEV double svar() const { return tstop - r; }   // the integration variable (Rejection: time)
     PDMP_DEV double threshold_time() const {
         if constexpr (SHADOW_T) return tacc;
         else if constexpr (ALG == PDMP_ALG_CHV) return (double)y[D - 1];
-        else return s;
+        else return svar();
     }
     PDMP_DEV bool sample_due(const KParams& P) const {
         if constexpr (!STATS) return false;
@@ -337,14 +342,16 @@ struct Traj {
 #pragma unroll
         for (int i = 0; i < ND; ++i) xd[i] = (int)P.xd0[(P.xd0_per_traj ? (size_t)idx * ND : 0) + i];
         const double E0 = -log(draw(P, exhausted));  // tstop_extended = -log(rand())
+        double s0;
         if constexpr (ALG == PDMP_ALG_CHV) {
             y[NC] = (R)P.t0;  // X_extended[end] = ti
-            s = 0.0;
+            s0 = 0.0;
             tstop = E0;
         } else {
-            s = P.t0;
+            s0 = P.t0;
             tstop = E0 / (double)M::bound(y, xd, P.parms, (R)P.t0) + P.t0;  // src/rejectiondiffeq.jl:105-107
         }
+        r = tstop - s0;
         tacc = P.t0;
         tlast = P.t0; ts = P.t0;
         simnj = 1; nfict = 0;
@@ -357,7 +364,7 @@ struct Traj {
 
         // Hairer-Norsett-Wanner initial step (OrdinaryDiffEq ode_determine_initdt), order 5
         refresh_rate(P, P.t0);
-        field(P, y, k1, (R)s);
+        field(P, y, k1, (R)s0);
         double d0 = 0.0, d1 = 0.0;
         double sk[D];
 #pragma unroll
@@ -372,7 +379,7 @@ struct Traj {
         R u1[D], f1[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) u1[i] = fma((R)dt0, k1[i], y[i]);
-        field(P, u1, f1, (R)(s + dt0));
+        field(P, u1, f1, (R)(s0 + dt0));
         double d2 = 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) { const double a = ((double)f1[i] - (double)k1[i]) / sk[i]; d2 = fma(a, a, d2); }
@@ -419,10 +426,20 @@ struct Traj {
         R tot = rate[0];
 #pragma unroll
         for (int i = 1; i < NR; ++i) tot += rate[i];  // sum(rate), left to right
-        if (!(tot > R(0)) || isinf(tot)) { finish(P, PDMP_ST_NONPOSITIVE_RATE); return true; }
+        double u_exp;
         if (tj < P.tf) {  // :52
+            // a positive finite total is required where pfsample uses it; at the overshoot threshold the
+            // reference computes the rates and ignores them
+            if (!(tot > R(0) && tot < (sizeof(R) == 4 ? (R)3.4028234e38f : (R)1.7976931348623157e308))) {
+                finish(P, PDMP_ST_NONPOSITIVE_RATE); return true;
+            }
+            // rand() of pfsample then rand() of :71 = the cached half of the previous Philox block and the
+            // first half of a new one: ONE Philox call, no parity branch (DrawStream::next2)
+            double u_ev;
+            rng.next2(P.rng_mode, P.replay_u + (size_t)lid * P.replay_stride, P.replay_stride, P.traj_id_offset + lid, P.keys,
+                      ex, u_ev, u_exp);
             // pfsample, reference src/utils.jl:46-57 (strict <, last index absorbs round-off)
-            const R thr = (R)draw(P, ex) * tot;
+            const R thr = (R)u_ev * tot;
             int ev = 1;
             R cw = rate[0];
 #pragma unroll
@@ -433,14 +450,20 @@ struct Traj {
             for (int i = 0; i < ND; ++i) xd[i] += P.nu[(ev - 1) * ND + i];
             if constexpr (M::HAS_DELTA) M::delta(y, xd, P.parms, tj, ev);
             refresh_rate(P, tj);
-            field(P, y, k1, (R)s);  // u_modified!(integrator, true): FSAL re-evaluated
+            field(P, y, k1, (R)tstop);  // u_modified!(integrator, true): FSAL re-evaluated (s = tstop here)
 #pragma unroll
             for (int i = 0; i < NC; ++i) xs[i] = y[i];  // caract.xc .= u
             ts = tj;
             ++jumps;
+        } else {
+            u_exp = draw(P, ex);          // the overshoot threshold draws its exponential only
         }
         ++simnj;                          // :70
-        tstop += -log(draw(P, ex));       // :71, always drawn
+        {
+            const double tnew = tstop - log(u_exp);   // :71, always drawn
+            r = tnew - tstop;                         // s sits exactly on the old threshold
+            tstop = tnew;
+        }
         if (!(tlast < tj)) { finish(P, PDMP_ST_NO_PROGRESS); return true; }  // @assert :145
         tlast = tj;                       // :146
         if (P.save_post && tj <= P.tf) write_record(P, tj, xs);  // :149-156
@@ -451,7 +474,7 @@ struct Traj {
     PDMP_DEV bool rej_candidate(const KParams& P, unsigned& aux, unsigned& jumps) {
         int fail = PDMP_ST_OK;
         bool ex = false;
-        const double tc = s;
+        const double tc = tstop;    // the candidate time: the lane landed, s == tstop
         R rate[NR];
         M::rates(rate, y, xd, P.parms, (R)tc);
         R tot = rate[0];
@@ -475,7 +498,7 @@ struct Traj {
 #pragma unroll
             for (int i = 0; i < ND; ++i) xd[i] += P.nu[(ev - 1) * ND + i];
             if constexpr (M::HAS_DELTA) M::delta(y, xd, P.parms, tc, ev);
-            field(P, y, k1, (R)s);
+            field(P, y, k1, (R)tc);
             ++simnj;                                         // :64
             ++jumps;
         } else {
@@ -486,7 +509,8 @@ struct Traj {
             for (int i = 0; i < NC; ++i) xs[i] = y[i];
             ts = tc;
         }
-        tstop += dtn;                                        // :71
+        tstop = tc + dtn;                                    // :71
+        r = tstop - tc;
         if (tlast >= tc) { finish(P, PDMP_ST_NO_PROGRESS); return true; }  // :121-124
         tlast = tc;
         if (P.save_post && tc <= P.tf && !reject) write_record(P, tc, y);  // :128-138
@@ -572,7 +596,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
                     // while (t < tf) && (njumps < n_jumps): may be false before the first step
                     if (!(tr.simnj < P.n_jumps)) tr.finish(P, PDMP_ST_HIT_NJUMPS);
                     else if (ex) tr.finish(P, PDMP_ST_REPLAY_EXHAUSTED);
-                    else if (NO_FLOW) { tr.s = tr.tstop; st = LANE_WAIT; }
+                    else if (NO_FLOW) { tr.r = 0.0; st = LANE_WAIT; }
                     else st = LANE_RUN;
                 } else {
                     st = LANE_EXHAUSTED;
@@ -596,14 +620,14 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
             if (st == LANE_WAIT) {
                 bool done;
                 if (fc) { tr.finish(P, fc); done = true; }
-                else if (!NO_FLOW && tr.s != tr.tstop) done = false;   // stopped for a sample only: back to stepping
+                else if (!NO_FLOW && tr.r != 0.0) done = false;   // stopped for a sample only: back to stepping
                 else {
                     ++c_cands;
                     if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, c_aux, c_jumps);
                     else done = tr.rej_candidate(P, c_aux, c_jumps);
                 }
-                if (done) st = LANE_DEAD;
-                else if (NO_FLOW) { tr.s = tr.tstop; }   // F = F_dummy: next candidate directly
+                if (done) { st = LANE_DEAD; c_attempts += tr.attempts; }
+                else if (NO_FLOW) { tr.r = 0.0; }   // F = F_dummy: next candidate directly
                 else st = LANE_RUN;
             }
             continue;
@@ -617,67 +641,64 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
         if constexpr (!NO_FLOW) {
         const int not_run0 = 32 - n_run;
         const int thr = P.jump_thresh > 0 ? min(P.jump_thresh, (n_live + 1) >> 1) : 1;
-        unsigned att = 0;
+        // OrdinaryDiffEq snaps to a tstop that is within 100 eps of the step's end
+        const double snaptol = 2.220446049250313e-14 * fabs(tr.tstop);
         for (;;) {
         if (st == LANE_RUN) {
             const double hprop = tr.h;
-            double step = hprop;
-            bool clipped = false;
-            const double rem = tr.tstop - tr.s;
-            if (step >= rem) { step = rem; clipped = true; }
+            const bool clipped = hprop >= tr.r;              // tstops: the step ends on the threshold
+            const double step = clipped ? tr.r : hprop;
             R yn[D], k7[D], inc, e2;
             if constexpr (ALG == PDMP_ALG_CHV && ChvSigned<M>::value) {
-                R c[D], g7;
-                M::chv_signs(c, tr.xd, P.parms);
-                e2 = rk_attempt_signed<Tab, D, R>([&](const R* x) { return M::chv_scalar(x, tr.xd, P.parms); }, c, tr.y,
-                                                  tr.k1[D - 1], (R)tr.s, (R)step, yn, g7, (R)P.reltol, (R)P.abstol, inc);
+                R g7;
+                const unsigned neg = M::chv_negmask(tr.xd, P.parms);
+                e2 = rk_attempt_signed<Tab, D, R>([&](const R* x) { return M::chv_scalar(x, tr.xd, P.parms); }, neg, tr.y,
+                                                  tr.k1[D - 1], R(0), (R)step, yn, g7, (R)P.reltol, (R)P.abstol, inc);
 #pragma unroll
-                for (int i = 0; i < D; ++i) k7[i] = c[i] * g7;
+                for (int i = 0; i < D; ++i) k7[i] = apply_sign(g7, neg, i);
             } else {
                 auto rhs = [&](const R* x, R* dx, R t) { tr.field(P, x, dx, t); };
-                e2 = rk_attempt<Tab, D, R>(rhs, tr.y, tr.k1, (R)tr.s, (R)step, yn, k7, (R)P.reltol, (R)P.abstol, inc);
+                e2 = rk_attempt<Tab, D, R>(rhs, tr.y, tr.k1, (R)tr.svar(), (R)step, yn, k7, (R)P.reltol, (R)P.abstol, inc);
             }
-            ++att;
-            const bool accept = e2 <= (R)D;
-            double hnext;
-            if (e2 < (sizeof(R) == 4 ? (R)3.4028234e38f : (R)1.7976931348623157e308)) {  // finite (false for NaN and Inf)
-                hnext = step * (double)tr.pi.step((float)(e2 * (R)(1.0 / D)), accept);
-            } else {
-                // trial step left the domain of F/R: reject with the maximal shrink (what
-                // OrdinaryDiffEq does with an infinite estimate); fatal only if the accepted
-                // state itself is non-finite or the step no longer advances s
-                bool ok = true;
+            ++tr.attempts;
+            if (e2 <= (R)D) {                                // accepted (false for a NaN estimate)
 #pragma unroll
-                for (int i = 0; i < D; ++i) ok = ok && isfinite(tr.y[i]) && isfinite(tr.k1[i]);
-                hnext = 0.2 * step;
-                if (!ok || !(tr.s + hnext > tr.s)) { tr.finish(P, PDMP_ST_NAN); st = LANE_DEAD; }
-            }
-            if (st == LANE_RUN && ++tr.attempts > budget) { tr.finish(P, PDMP_ST_MAX_ATTEMPTS); st = LANE_DEAD; }
-            if (st == LANE_RUN) {
-                if (accept) {
-#pragma unroll
-                    for (int i = 0; i < D; ++i) { tr.y[i] = yn[i]; tr.k1[i] = k7[i]; }
-                    if constexpr (T::SHADOW_T) { tr.tacc += (double)inc; tr.y[D - 1] = (R)tr.tacc; }
-                    // tstop reached: exactly (clipped step) or within 100 eps (OrdinaryDiffEq's
-                    // floating-point snap; here step < rem, so the gap is rem - step)
-                    double sn = tr.s + step;
-                    if (clipped || rem - step < 2.220446049250313e-14 * fabs(tr.tstop)) {
-                        sn = tr.tstop;
-                        st = LANE_WAIT;
-                    }
-                    tr.s = sn;
-                    if constexpr (STATS) if (tr.sample_due(P)) st = LANE_WAIT;   // stepped past a sample time
-                    if (clipped && P.tstop_policy == 1) hnext = fmax(hnext, hprop);
+                for (int i = 0; i < D; ++i) { tr.y[i] = yn[i]; tr.k1[i] = k7[i]; }
+                if constexpr (T::SHADOW_T) { tr.tacc += (double)inc; tr.y[D - 1] = (R)tr.tacc; }
+                double hnext = step * (double)tr.pi.template accept<D>((float)e2);
+                const double r2 = tr.r - step;
+                // threshold reached: exactly (clipped step) or within 100 eps (the floating-point snap)
+                if (clipped || r2 < snaptol) {
+                    tr.r = 0.0;
+                    st = LANE_WAIT;
+                    if (clipped && P.tstop_policy == 1 && hnext < hprop) hnext = hprop;
                 } else {
-                    ++c_rejects;
+                    tr.r = r2;
                 }
                 tr.h = hnext;
+                if constexpr (STATS && !ConstFlow<M>::value) if (tr.sample_due(P)) st = LANE_WAIT;   // stepped past a sample time
+            } else {
+                ++c_rejects;
+                if (e2 < (sizeof(R) == 4 ? (R)3.4028234e38f : (R)1.7976931348623157e308)) {
+                    tr.h = step * (double)tr.pi.template reject<D>((float)e2);
+                } else {
+                    // trial step left the domain of F/R (non-finite estimate): reject with the maximal shrink,
+                    // what OrdinaryDiffEq does with an infinite estimate; fatal only if the accepted state
+                    // itself is non-finite or the step no longer advances s
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) ok = ok && isfinite(tr.y[i]) && isfinite(tr.k1[ChvSigned<M>::value ? D - 1 : i]);
+                    tr.h = 0.2 * step;
+                    const double sv = tr.svar();
+                    if (!ok || !(sv + tr.h > sv)) { tr.finish(P, PDMP_ST_NAN); st = LANE_DEAD; c_attempts += tr.attempts; }
+                }
             }
+            // OrdinaryDiffEq's maxiters: the budget is spent and the threshold is still ahead
+            if (st == LANE_RUN && tr.attempts >= budget) { tr.finish(P, PDMP_ST_MAX_ATTEMPTS); st = LANE_DEAD; c_attempts += tr.attempts; }
         }
         const int left = __popc(__ballot_sync(0xffffffffu, st != LANE_RUN)) - not_run0;   // lanes that landed (or failed)
         if (n_wait + left >= thr || left == n_run) break;
         }
-        c_attempts += att;
         }
     }
 
@@ -693,8 +714,12 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
     if (STATS && P.stats_in_smem) {
         __syncthreads();
         const int nd = 3 * P.n_sample * P.n_comp, nh = P.n_sample * P.hist_n * P.hist_bins;
-        for (int i = threadIdx.x; i < nd; i += BLOCK)
-            if (sstat[i] != 0.0) atomicAdd(P.stats + i, sstat[i]);
+        const int TC = P.n_sample * P.n_comp;
+        for (int i = threadIdx.x; i < nd; i += BLOCK) {
+            // counts: one integer per sample time in the slot of component 0, broadcast to all components
+            const double v = i < TC ? (double)*reinterpret_cast<const unsigned*>(sstat + (i / P.n_comp) * P.n_comp) : sstat[i];
+            if (v != 0.0) atomicAdd(P.stats + i, v);
+        }
         for (int i = threadIdx.x; i < nh; i += BLOCK)
             if (shist[i]) atomicAdd(P.hist + i, (unsigned long long)shist[i]);
     }

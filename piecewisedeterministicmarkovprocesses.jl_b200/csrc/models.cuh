@@ -45,10 +45,8 @@ struct TcpDev {  // examples/tcp.jl:25-45
     template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
     // (F, 1) / (1/x) = (±1, 1) * x : a sign vector times a scalar (rk_attempt_signed, device_core.cuh)
     static constexpr bool CHV_SIGNED_SCALAR = true;
-    template <class R> PDMP_DEV static void chv_signs(R* c, const int* xd, const double* p) {
-        c[0] = (R)(1 - 2 * (xd[0] & 1));
-        c[1] = R(1);
-    }
+    // the sign vector as a bit mask (bit i set: component i of the field is -g): (-1)^xd[1] on x, +1 on t
+    PDMP_DEV static unsigned chv_negmask(const int* xd, const double* p) { return (unsigned)(xd[0] & 1); }
     template <class R> PDMP_DEV static R chv_scalar(const R* y, const int* xd, const double* p) { return y[0]; }
     template <class R> PDMP_DEV static void chv_field(R* dy, const R* y, const int* xd, const double* p) {
         const R sg = (R)(1 - 2 * (xd[0] & 1));  // hoisted out of the stage loop by the compiler
