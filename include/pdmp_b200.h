@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PDMP_ABI_VERSION 7
+#define PDMP_ABI_VERSION 8
 
 /* ---- enumerations ------------------------------------------------------------------ */
 
@@ -94,7 +94,7 @@ typedef struct pdmp_model_info {
     int32_t has_delta;  /* model has a Delta(xc, xd, p, t, ev) acting after nu            */
     int32_t zero_flow;  /* F == F_dummy (reference src/problem.jl:4-7)                    */
     int32_t exact_flow; /* the functor is an exact flow Phi: PDMP_ALG_REJECTION_EXACT only   */
-    int32_t reserved0;
+    int32_t composite;  /* R is split into a constant and a variable part: rate_kind 2 usable  */
     char name[32];
 } pdmp_model_info;
 
@@ -121,7 +121,12 @@ typedef struct pdmp_problem_desc {
                                     between jumps; the CHV field re-uses the value computed at the
                                     post-jump state instead of re-evaluating R at every stage.
                                     Only for models whose rates depend on xd alone
-                                    (PDMP_ERR_UNSUPPORTED otherwise: it would change results)   */
+                                    (PDMP_ERR_UNSUPPORTED otherwise: it would change results)
+                                 2: CompositeRate (src/rate.jl:42-69): a ConstantRate part, cached from
+                                    jump to jump, plus a VariableRate part evaluated at every stage.
+                                    Only for models registered with such a split (composite = 1 in
+                                    pdmp_model_info); results identical to rate_kind 0
+                                    (test/testRatesComposite.jl:95-105)                         */
 } pdmp_problem_desc;
 
 /* Mirrors the keyword arguments of the reference `solve` (src/chvdiffeq.jl:187-219,
@@ -158,9 +163,12 @@ typedef struct pdmp_solve_opts {
                                         h_clipped/q (OrdinaryDiffEq behaviour)
                                      1: additionally never propose less than the unclipped
                                         proposal that was pending before the clip          */
-    int32_t ref_quirks;           /* oracle only: 1 reproduces the reference's last-bit at
-                                     default tolerances 1e-3/1e-6 (src/chvdiffeq.jl:160-168)
-                                     and the stale-xc last bit of rejection_diffeq!        */
+    int32_t ref_quirks;           /* 1: the final point at t = tf exactly as the reference computes it
+                                     (src/chvdiffeq.jl:160-168, src/rejectiondiffeq.jl:142-150): a fresh
+                                     plain-F solve at OrdinaryDiffEq's DEFAULT tolerances 1e-3 / 1e-6 with
+                                     its automatic initial step, from caract.xc (the state at the last
+                                     executed jump) at time tprev (the previous threshold / candidate).
+                                     0: the same flow at the caller's tolerances, consistent anchor   */
     int32_t xd_bytes;             /* width of the saved discrete states in result.xd:
                                      0 or 8: int64 (the reference's Int64 layout)
                                      4: int32 — always exact (the kernel holds xd as int32)
@@ -173,6 +181,20 @@ typedef struct pdmp_solve_opts {
                                      continuous / save_d_count discrete components of every  */
     int32_t save_d_count;         /* point (0: all — the reference saves all of them,
                                      src/rejection.jl:32); result.n_c / n_d report the counts */
+    /* ---- ABI v8 ---- */
+    const int32_t* devices;       /* [n_devices] CUDA ordinals: the ensemble is sharded over them by
+                                     contiguous global id range, one host thread per device, statistics
+                                     summed in the library; NULL / n_devices <= 1: `device` alone.  An
+                                     ordinal may be listed more than once (several shards on one GPU). */
+    uint64_t save_c_mask;         /* ind_save_c / ind_save_d of the reference (src/chv.jl:54-62, doc    */
+    uint64_t save_d_mask;         /* src/chvdiffeq.jl:200-201) as bit masks: bit j set = component j is
+                                     saved; 0 = all.  result.n_c / n_d are the saved counts and the
+                                     columns of result.xc / xd follow increasing j                     */
+    int32_t n_devices;
+    int32_t save_rate;            /* 1: result.rate[k] = total rate at the pre-jump state of the jump
+                                     that produced saved point k (reference save_rate / rate_hist,
+                                     src/chvdiffeq.jl:47,54, src/rejectiondiffeq.jl:134); NaN for the
+                                     initial and the final point                                       */
 } pdmp_solve_opts;
 
 /* ---- result ------------------------------------------------------------------------ */
@@ -210,6 +232,16 @@ typedef struct pdmp_result {
     int32_t n_c, n_d;
     int32_t xd_bytes, reserved0;
     void* owner;               /* private                                                  */
+    /* ---- ABI v8 ---- */
+    double* rate;              /* [total_records] when opts.save_rate, else NULL           */
+    /* Multi-device runs (opts.n_devices > 1): one block per device shard, each a complete
+     * pdmp_result for trajectories [traj_begin, traj_begin + n_traj) with its own CSR arrays;
+     * the top-level arrays offsets/time/xc/xd/rate/njumps/nrejected/status are then NULL, the
+     * counters and statistics above are the sums over the blocks (summed in block order).   */
+    struct pdmp_result* blocks;
+    uint64_t traj_begin;       /* global index of this block's first trajectory (0 at top level) */
+    int32_t n_blocks;          /* 0: single device                                         */
+    int32_t device;            /* device this result / block ran on                        */
 } pdmp_result;
 
 /* ---- entry points ------------------------------------------------------------------ */

@@ -22,7 +22,7 @@ using Libdl
 
 export CHVGPU, RejectionGPU, RejectionExactGPU, EnsembleResult, device_count, list_models
 
-const ABI_VERSION = 7
+const ABI_VERSION = 8
 const libpdmp = Ref{String}(get(ENV, "PDMP_B200_LIB", "libpdmp_b200.so"))
 
 # ---- algorithm types ---------------------------------------------------------------------
@@ -84,7 +84,7 @@ struct ModelInfo
     has_delta::Int32
     zero_flow::Int32
     exact_flow::Int32
-    reserved0::Int32
+    composite::Int32
     name::NTuple{32, UInt8}
 end
 
@@ -134,6 +134,11 @@ struct SolveOpts
     xd_bytes::Int32
     save_c_count::Int32
     save_d_count::Int32
+    devices::Ptr{Int32}
+    save_c_mask::UInt64
+    save_d_mask::UInt64
+    n_devices::Int32
+    save_rate::Int32
 end
 
 mutable struct CResult
@@ -169,6 +174,11 @@ mutable struct CResult
     xd_bytes::Int32
     reserved0::Int32
     owner::Ptr{Cvoid}
+    rate::Ptr{Float64}
+    blocks::Ptr{Cvoid}
+    traj_begin::UInt64
+    n_blocks::Int32
+    device::Int32
     CResult() = new()
 end
 
@@ -219,12 +229,17 @@ struct EnsembleResult
     hist::Array{UInt64, 3}        # bins × hist_n × T
     counters::NamedTuple
     save_positions::Tuple{Bool, Bool}
+    rate::Vector{Float64}         # save_rate: total rate at the jump behind every saved point (NaN: none)
 end
 
 Base.length(r::EnsembleResult) = length(r.njumps)
 function Base.getindex(r::EnsembleResult, i::Integer)
     a, b = Int(r.offsets[i]) + 1, Int(r.offsets[i+1])
-    PDMP.PDMPResult(r.time[a:b], r.xc[:, a:b], r.xd[:, a:b], Float64[], r.save_positions,
+    # PDMPResult.rates: one entry per saved jump after the initial slot (which the reference leaves
+    # uninitialised, src/problem.jl:158); the final point at tf has no entry there
+    rates = isempty(r.rate) ? Float64[] : r.rate[a:b]
+    (length(rates) > 1 && isnan(rates[end])) && pop!(rates)
+    PDMP.PDMPResult(r.time[a:b], r.xc[:, a:b], r.xd[:, a:b], rates, r.save_positions,
                     r.njumps[i], r.nrejected[i])
 end
 
@@ -233,7 +248,7 @@ _copy(p::Ptr{T}, dims...) where {T} = (p == C_NULL || prod(dims) == 0) ? zeros(T
 
 # saved discrete states arrive as Int64, or narrower under `xd_bytes = 4 | 2` (less PCIe traffic);
 # they are widened here to the reference's Int64
-function _xd(res::CResult, tot::Int)
+function _xd(res, tot::Int)
     nd = Int(res.n_d)
     (res.xd == C_NULL || tot == 0) && return zeros(Int64, nd, tot)
     T = res.xd_bytes == 2 ? Int16 : res.xd_bytes == 4 ? Int32 : Int64
@@ -249,7 +264,9 @@ Keyword arguments of the reference `solve` keep their meaning (`n_jumps`, `save_
 `trajectories`, `seed`, `replay` (draws × trajectories matrix of uniforms, consumed in the
 reference's order), `sample_times`, `hist = [(component, lo, hi), ...]`, `hist_bins`, `device`,
 `traj_id_offset`, `xc0` / `xd0` (n_c × trajectories per-trajectory initial conditions),
-`max_records`, `no_records`.
+`max_records`, `no_records`, `devices` (vector of CUDA ordinals: the ensemble is sharded over them inside the
+library call, statistics summed there), `save_rate`, `ind_save_c` / `ind_save_d` (1-based component indices,
+reference src/chv.jl:54-62), `ref_quirks` (the final point at `tf` computed exactly like the reference's last bit).
 `problem.caract.F/R` are not called: the device functor named by `algo.model` is.
 Per-trajectory failures (the reference's `@assert`s, src/chvdiffeq.jl:145,
 src/rejectiondiffeq.jl:33) are returned in `status`, never thrown.
@@ -260,8 +277,10 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
                          sample_times = Float64[], hist = Tuple{Int, Float64, Float64}[], hist_bins = 0,
                          device = 0, traj_id_offset = 0, xc0 = nothing, xd0 = nothing, max_records = 0,
                          no_records = false, max_attempts = 0, tstop_policy = 0, xd_bytes = 8,
-                         save_c_count = 0, save_d_count = 0,
-                         verbose = false, save_rate = false, finalizer = nothing, kwargs...)
+                         save_c_count = 0, save_d_count = 0, devices = Int[], ind_save_c = nothing, ind_save_d = nothing,
+                         ref_quirks = false, verbose = false,
+                         save_rate = algo isa RejectionGPU,   # the reference's defaults: src/chvdiffeq.jl:218, src/rejectiondiffeq.jl:162
+                         finalizer = nothing, kwargs...)
     (n_jumps === nothing || !isfinite(n_jumps)) &&
         error("n_jumps must be given and finite for an ensemble solve")
     finalizer === nothing || error("finalizer is a Julia closure (src/chvdiffeq.jl:157): not portable to the device")
@@ -282,13 +301,16 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
     st = Vector{Float64}(sample_times)
     hc = Int32[h[1] - 1 for h in hist]; hlo = Float64[h[2] for h in hist]; hhi = Float64[h[3] for h in hist]
     ru = replay === nothing ? Float64[] : Matrix{Float64}(replay)
+    dv = Vector{Int32}(devices)
+    _mask(ind) = ind === nothing ? UInt64(0) : reduce(|, (UInt64(1) << (Int(i) - 1) for i in ind); init = UInt64(0))
+    rate_kind = car.R isa PDMP.ConstantRate ? 1 : car.R isa PDMP.CompositeRate ? 2 : 0   # src/rate.jl:17-69
 
     res = CResult()
-    GC.@preserve xc xd nu parms st hc hlo hhi ru begin
+    GC.@preserve xc xd nu parms st hc hlo hhi ru dv begin
         desc = ProblemDesc(trajectories, traj_id_offset, pointer(xc), pointer(xd), pointer(nu),
                            isempty(parms) ? C_NULL : pointer(parms), problem.tspan[1], problem.tspan[2],
                            info.id, xc0 === nothing ? 0 : 1, xd0 === nothing ? 0 : 1, 1, length(parms),
-                           car.R isa PDMP.ConstantRate ? 1 : 0)   # ConstantRate wrapper (src/rate.jl:17-40)
+                           rate_kind)
         function opts(maxrec)
             SolveOpts(reltol, abstol, Int64(n_jumps), max_attempts, UInt64(seed),
                       isempty(ru) ? C_NULL : pointer(ru), isempty(ru) ? 0 : size(ru, 1),
@@ -296,7 +318,9 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
                       isempty(hlo) ? C_NULL : pointer(hlo), isempty(hhi) ? C_NULL : pointer(hhi), maxrec,
                       algorithm_code(algo), ode_code(algo), precision_code(algo), isempty(ru) ? 0 : 1,
                       save_positions[1], save_positions[2], no_records, length(st), length(hc),
-                      isempty(hc) ? 0 : hist_bins, device, tstop_policy, 0, xd_bytes, save_c_count, save_d_count)
+                      isempty(hc) ? 0 : hist_bins, isempty(dv) ? device : dv[1], tstop_policy, ref_quirks, xd_bytes,
+                      save_c_count, save_d_count, isempty(dv) ? C_NULL : pointer(dv), _mask(ind_save_c), _mask(ind_save_d),
+                      length(dv), save_rate)
         end
         rc = ccall((:pdmp_solve_ensemble, libpdmp[]), Int32, (Ref{ProblemDesc}, Ref{SolveOpts}, Ref{CResult}),
                    desc, opts(max_records), res)
@@ -310,15 +334,23 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
     end
     n, tot = Int(res.n_traj), Int(res.total_records)
     T, C, H, B = Int(res.n_sample_times), Int(res.n_comp), Int(res.hist_n), Int(res.hist_bins)
-    out = EnsembleResult(_copy(res.offsets, n + 1), _copy(res.time, tot),
-                         _copy(res.xc, Int(res.n_c), tot), _xd(res, tot),
-                         _copy(res.njumps, n), _copy(res.nrejected, n), _copy(res.status, n),
+    # a multi-device run returns one block per device shard (pdmp_result.blocks): concatenate, offsets rebased
+    blocks = res.n_blocks > 1 ? [unsafe_load(Ptr{CResult}(res.blocks), g) for g in 1:Int(res.n_blocks)] : [res]
+    base = cumsum([0; [Int(b.total_records) for b in blocks]])
+    offs = vcat([_copy(b.offsets, Int(b.n_traj) + 1)[1:end-1] .+ UInt64(base[g]) for (g, b) in enumerate(blocks)]..., UInt64[base[end]])
+    cat1(f) = vcat([f(b) for b in blocks]...)
+    cat2(f) = hcat([f(b) for b in blocks]...)
+    out = EnsembleResult(offs, cat1(b -> _copy(b.time, Int(b.total_records))),
+                         cat2(b -> _copy(b.xc, Int(res.n_c), Int(b.total_records))), cat2(b -> _xd(b, Int(b.total_records))),
+                         cat1(b -> _copy(b.njumps, Int(b.n_traj))), cat1(b -> _copy(b.nrejected, Int(b.n_traj))),
+                         cat1(b -> _copy(b.status, Int(b.n_traj))),
                          _copy(res.stat_count, C, T), _copy(res.stat_sum, C, T), _copy(res.stat_sumsq, C, T),
                          _copy(res.hist, B, H, T),
                          (rk_attempts = res.rk_attempts, rk_rejects = res.rk_rejects, aux_attempts = res.aux_attempts,
                           total_jumps = res.total_jumps, total_candidates = res.total_candidates,
                           kernel_ms = res.kernel_ms, compact_ms = res.compact_ms, h2d_ms = res.h2d_ms, d2h_ms = res.d2h_ms),
-                         (Bool(save_positions[1]), Bool(save_positions[2])))
+                         (Bool(save_positions[1]), Bool(save_positions[2])),
+                         save_rate ? cat1(b -> _copy(b.rate, Int(b.total_records))) : Float64[])
     ccall((:pdmp_result_free, libpdmp[]), Cvoid, (Ref{CResult},), res)
     out
 end

@@ -226,6 +226,23 @@ struct RatesCstModel {  // test/testRatesCst.jl:5-24 (rates constant between jum
     }
     static void Delta(double*, int64_t*, const double*, double, int) {}
 };
+struct RatesCompositeModel {  // test/testRatesComposite.jl:5-45: R!, and its split Rcst! + Rvar! for CompositeRate
+    static constexpr int NC = 1, ND = 2, NR = 2, NP = 1;
+    static constexpr bool HAS_BOUND = false, HAS_DELTA = false, ZERO_FLOW = false, COMPOSITE = true;
+    static constexpr const char* NAME = "rates_composite";
+    static double Rx(double x) { return 10.0 + x; }                                                   // R(x), :14
+    static void F(double* xdot, const double* xc, const int64_t* xd, const double* p, double t) { StiffModel::F(xdot, xc, xd, p, t); }
+    static void R(double* rate, const double* xc, const int64_t* xd, const double*, double, bool issum, double* out) {  // R!, :16-25
+        if (!issum) { rate[0] = Rx(xc[0]); rate[1] = (double)xd[1]; out[0] = 0.0; out[1] = 0.0; }
+        else { out[0] = Rx(xc[0]) + (double)xd[1]; out[1] = out[0]; }
+    }
+    static double Rcst(const double*, const int64_t* xd, const double*, double) { return (double)xd[1]; }   // Rcst!(..., true), :27-36
+    static double Rvar(const double* xc, const int64_t*, const double*, double) { return Rx(xc[0]); }       // Rvar!(..., true), :38-47
+    static void Delta(double*, int64_t*, const double*, double, int) {}
+};
+template <class M, class = void> struct IsComposite { static constexpr bool value = false; };
+template <class M> struct IsComposite<M, decltype((void)M::COMPOSITE)> { static constexpr bool value = M::COMPOSITE; };
+
 struct NeuronEvaModel {  // examples/pdmp_example_eva.jl:5-45 (Delta acting on xc)
     static constexpr int NC = 1, ND = 2, NR = 3, NP = 1;
     static constexpr bool HAS_BOUND = true, HAS_DELTA = true, ZERO_FLOW = false;
@@ -455,7 +472,7 @@ inline int pfsample(const double* w, int n, double U) {
     return i;
 }
 
-struct Record { double t; double xc[MAXC]; int64_t xd[MAXD]; };
+struct Record { double t; double xc[MAXC]; int64_t xd[MAXD]; double rate; };
 
 struct TrajOut {
     std::vector<Record>* recs;
@@ -550,10 +567,12 @@ struct Sampler {
     }
 };
 
-inline void push_record(TrajOut& out, int nc, int nd, double t, const double* xc, const int64_t* xd) {
+inline void push_record(TrajOut& out, int nc, int nd, double t, const double* xc, const int64_t* xd,
+                        double rate = std::numeric_limits<double>::quiet_NaN()) {
     if (!out.recs) return;
     Record r;
     r.t = t;
+    r.rate = rate;   // save_rate: total rate at the jump behind this point (reference rate_hist); NaN: none
     for (int i = 0; i < nc; ++i) r.xc[i] = xc[i];
     for (int i = 0; i < nd; ++i) r.xd[i] = xd[i];
     out.recs->push_back(r);
@@ -591,10 +610,17 @@ void chv_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut& out,
 
     double rate[MAXR];
     // (chv::CHV)(xdot, x, caract, t), src/chvdiffeq.jl:6-16
+    // CompositeRate (src/rate.jl:42-69): the ConstantRate part caches its total until the next R(..., false) call
+    double cst_cache = -1.0;
     auto field = [&](double* xdot, const double* x, double /*s*/) {
         const double tau = x[NC];
         double rr[2];
-        M::R(rate, x, xd, p, tau, true, rr);
+        if constexpr (IsComposite<M>::value) {
+            if (d.rate_kind == 2) {
+                if (cst_cache < 0) cst_cache = M::Rcst(x, xd, p, tau);   // src/rate.jl:28-33
+                rr[0] = cst_cache + M::Rvar(x, xd, p, tau);              // out_cst .+ out_var, :65-67
+            } else M::R(rate, x, xd, p, tau, true, rr);
+        } else M::R(rate, x, xd, p, tau, true, rr);
         const double sr = rr[0];  // the reference divides blindly; error control rejects bad stages
         M::F(xdot, x, xd, p, tau);
         xdot[NC] = 1.0;
@@ -618,11 +644,14 @@ void chv_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut& out,
         // ensemble extension: sample times in (tprev, min(tj, tf)] see the pre-jump xd and
         // the plain-F flow from the last post-jump state (generalised "last bit")
         if (!smp.sample_until(std::min(tj, tf), xd, p, max_attempts, &fs)) { out.status = (uint8_t)fs; break; }
-        if (o.save_pre && tj <= tf) push_record(out, NC, ND, tj, it.u, xd);  // :41-48
         {
             double rr[2];
             M::R(rate, it.u, xd, p, tj, false, rr);  // :51, rates at the PRE-jump state
+            cst_cache = -1.0;                        // ConstantRate: R(..., false) drops the cached total (src/rate.jl:35-38)
         }
+        double tot_here = rate[0];
+        for (int k = 1; k < NR; ++k) tot_here += rate[k];
+        if (o.save_pre && tj <= tf) push_record(out, NC, ND, tj, it.u, xd, tot_here);  // :41-48
         if (tj < tf) {                                  // :52
             // docs/src/solver.md:41-42 requires a positive total rate; the reference would
             // sample from an all-zero / NaN vector here, we flag the trajectory instead.  Only where
@@ -645,7 +674,7 @@ void chv_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut& out,
         if (!(t < lastjumptime)) { out.status = PDMP_ST_NO_PROGRESS; break; }  // @assert :145
         tprev = t; t = lastjumptime;                    // :146
         if (njumps_saved < simnj && o.save_post && t <= tf) {  // :149
-            push_record(out, NC, ND, t, xc, xd);
+            push_record(out, NC, ND, t, xc, xd, tj < tf ? tot_here : std::numeric_limits<double>::quiet_NaN());
             ++njumps_saved;
         }
         if (rng.exhausted) { out.status = PDMP_ST_REPLAY_EXHAUSTED; break; }
@@ -727,9 +756,12 @@ void rejection_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut
         if (!(ppf[0] < ppf[1])) { out.status = PDMP_ST_BOUND_VIOLATED; break; }  // @assert :33
         reject = rng.next() < 1.0 - ppf[0] / ppf[1];      // :35
         const double dtn = -std::log(rng.next()) / ppf[1];  // :36
+        double tot_jump = std::numeric_limits<double>::quiet_NaN();
         if (tc < tf && !reject) {                         // :41
             double rr[2];
             M::R(rate, it.u, xd, p, tc, false, rr);       // :43
+            tot_jump = rate[0];
+            for (int k = 1; k < NR; ++k) tot_jump += rate[k];   // sum(ratecache.rate), the value save_rate pushes (:134)
             const int ev = pfsample(rate, NR, rng.next());  // :55
             for (int k = 0; k < ND; ++k) xd[k] += sh.nu[ev - 1][k];
             M::Delta(it.u, xd, p, tc, ev);
@@ -746,7 +778,7 @@ void rejection_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut
         if (t >= lastjumptime) { out.status = PDMP_ST_NO_PROGRESS; break; }  // :121-124
         tprev = t; t = lastjumptime;
         if (o.save_post && t <= tf && !reject) {          // :128
-            push_record(out, NC, ND, t, xc, xd);
+            push_record(out, NC, ND, t, xc, xd, tot_jump);
             reject = true;
         }
         if (rng.exhausted) { out.status = PDMP_ST_REPLAY_EXHAUSTED; break; }
@@ -778,7 +810,7 @@ void rejection_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut
 // ------------------------------------------------------------------------------------
 struct ResultOwner {
     std::vector<uint64_t> offsets;
-    std::vector<double> time, xc;
+    std::vector<double> time, xc, rate;
     std::vector<int64_t> xd, njumps, nrejected;
     std::vector<uint8_t> status;
     Stats stats;
@@ -856,7 +888,12 @@ int run_ensemble(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_resu
     for (auto& c : tctr) { attempts += c.attempts; rejects += c.rejects; aux += c.aux; jumps += c.jumps; cands += c.cands; }
     for (uint64_t i = 0; i < n; ++i) own->offsets[i + 1] = own->offsets[i] + tcount[i];
     const uint64_t total = own->offsets[n];
-    own->time.resize(total); own->xc.resize(total * M::NC); own->xd.resize(total * M::ND);
+    // ind_save_c / ind_save_d (src/chv.jl:54-62) as bit masks: the selected components in increasing order
+    int csel[MAXC], dsel[MAXD], nco = 0, ndo = 0;
+    for (int c = 0; c < M::NC; ++c) if (!o->save_c_mask || ((o->save_c_mask >> c) & 1)) csel[nco++] = c;
+    for (int c = 0; c < M::ND; ++c) if (!o->save_d_mask || ((o->save_d_mask >> c) & 1)) dsel[ndo++] = c;
+    own->time.resize(total); own->xc.resize(total * nco); own->xd.resize(total * ndo);
+    if (o->save_rate) own->rate.resize(total);
     {
         std::atomic<uint64_t> cur{0};
         auto copier = [&]() {
@@ -869,8 +906,9 @@ int run_ensemble(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_resu
                     const uint64_t off = own->offsets[i];
                     for (uint64_t k = 0; k < tcount[i]; ++k) {
                         own->time[off + k] = src[k].t;
-                        for (int c = 0; c < M::NC; ++c) own->xc[(off + k) * M::NC + c] = src[k].xc[c];
-                        for (int c = 0; c < M::ND; ++c) own->xd[(off + k) * M::ND + c] = src[k].xd[c];
+                        for (int c = 0; c < nco; ++c) own->xc[(off + k) * nco + c] = src[k].xc[csel[c]];
+                        for (int c = 0; c < ndo; ++c) own->xd[(off + k) * ndo + c] = src[k].xd[dsel[c]];
+                        if (o->save_rate) own->rate[off + k] = src[k].rate;
                     }
                 }
             }
@@ -901,7 +939,8 @@ int run_ensemble(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_resu
     res->rk_attempts = attempts; res->rk_rejects = rejects; res->aux_attempts = aux;
     res->total_jumps = jumps; res->total_candidates = cands;
     res->n_sample_times = sh.T; res->n_comp = sh.C; res->hist_n = sh.H; res->hist_bins = sh.B;
-    res->n_c = M::NC; res->n_d = M::ND;
+    res->n_c = nco; res->n_d = ndo;
+    res->rate = o->save_rate ? own->rate.data() : nullptr;
     res->xd_bytes = 8;  // the oracle always returns the reference's Int64 layout
     res->owner = own;
     return PDMP_OK;
@@ -912,10 +951,11 @@ void fill_info(int id, pdmp_model_info* out) {
     std::memset(out, 0, sizeof(*out));
     out->id = id; out->n_c = M::NC; out->n_d = M::ND; out->n_r = M::NR; out->n_parms = M::NP;
     out->has_bound = M::HAS_BOUND; out->has_delta = M::HAS_DELTA; out->zero_flow = M::ZERO_FLOW;
+    out->composite = IsComposite<M>::value;
     std::strncpy(out->name, M::NAME, sizeof(out->name) - 1);
 }
 
-constexpr int N_MODELS = 11;
+constexpr int N_MODELS = 12;
 
 template <class Fn>
 int dispatch_model(int id, Fn&& fn) {
@@ -931,6 +971,7 @@ int dispatch_model(int id, Fn&& fn) {
         case 8: return fn((NeuronEvaModel*)nullptr);
         case 9: return fn((StiffDeltaModel*)nullptr);
         case 10: return fn((RatesCstModel*)nullptr);
+        case 11: return fn((RatesCompositeModel*)nullptr);
         default: g_err = "unknown model id"; return PDMP_ERR_MODEL;
     }
 }

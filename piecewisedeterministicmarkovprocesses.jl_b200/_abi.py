@@ -1,11 +1,11 @@
-"""ctypes mirror of include/pdmp_b200.h (ABI version 7).
+"""ctypes mirror of include/pdmp_b200.h (ABI version 8).
 
 Pure declarations: no library is loaded here, so the oracle loader (oracle/oracle.py, test
 infrastructure) can share the struct layouts without touching the product library.
 """
 import ctypes as C
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 ALG_CHV, ALG_REJECTION, ALG_REJECTION_EXACT = 0, 1, 2
 ODE_DP5, ODE_TSIT5 = 0, 1
@@ -29,7 +29,7 @@ c_uint8_p = C.POINTER(C.c_uint8)
 class ModelInfo(C.Structure):
     _fields_ = [("id", C.c_int32), ("n_c", C.c_int32), ("n_d", C.c_int32), ("n_r", C.c_int32),
                 ("n_parms", C.c_int32), ("has_bound", C.c_int32), ("has_delta", C.c_int32),
-                ("zero_flow", C.c_int32), ("exact_flow", C.c_int32), ("reserved0", C.c_int32),
+                ("zero_flow", C.c_int32), ("exact_flow", C.c_int32), ("composite", C.c_int32),
                 ("name", C.c_char * 32)]
 
 
@@ -52,11 +52,16 @@ class SolveOpts(C.Structure):
                 ("no_records", C.c_int32), ("n_sample_times", C.c_int32), ("hist_n", C.c_int32),
                 ("hist_bins", C.c_int32), ("device", C.c_int32), ("tstop_policy", C.c_int32),
                 ("ref_quirks", C.c_int32), ("xd_bytes", C.c_int32),
-                ("save_c_count", C.c_int32), ("save_d_count", C.c_int32)]
+                ("save_c_count", C.c_int32), ("save_d_count", C.c_int32),
+                ("devices", c_int32_p), ("save_c_mask", C.c_uint64), ("save_d_mask", C.c_uint64),
+                ("n_devices", C.c_int32), ("save_rate", C.c_int32)]
 
 
 class Result(C.Structure):
-    _fields_ = [("n_traj", C.c_uint64), ("total_records", C.c_uint64), ("records_needed", C.c_uint64),
+    pass
+
+
+Result._fields_ = [("n_traj", C.c_uint64), ("total_records", C.c_uint64), ("records_needed", C.c_uint64),
                 ("offsets", c_uint64_p), ("time", c_double_p), ("xc", c_double_p), ("xd", C.c_void_p),
                 ("njumps", c_int64_p), ("nrejected", c_int64_p), ("status", c_uint8_p),
                 ("stat_count", c_double_p), ("stat_sum", c_double_p), ("stat_sumsq", c_double_p),
@@ -68,7 +73,9 @@ class Result(C.Structure):
                 ("n_sample_times", C.c_int32), ("n_comp", C.c_int32), ("hist_n", C.c_int32),
                 ("hist_bins", C.c_int32), ("n_c", C.c_int32), ("n_d", C.c_int32),
                 ("xd_bytes", C.c_int32), ("reserved0", C.c_int32),
-                ("owner", C.c_void_p)]
+                ("owner", C.c_void_p),
+                ("rate", c_double_p), ("blocks", C.POINTER(Result)), ("traj_begin", C.c_uint64),
+                ("n_blocks", C.c_int32), ("device", C.c_int32)]
 
 
 # every symbol include/pdmp_b200.h declares (tests check the built library exports all)

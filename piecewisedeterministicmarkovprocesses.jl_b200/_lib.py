@@ -8,7 +8,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpdmp_b200.so")
+# PDMP_B200_LIB selects another build of the same library (kernel A/B experiments: scripts/build_variant.py)
+LIB_PATH = os.environ.get("PDMP_B200_LIB") or os.path.join(_HERE, "libpdmp_b200.so")
 _LIB = None
 
 

@@ -21,7 +21,8 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
           n_jumps=None, save_positions=(False, True), reltol=1e-7, abstol=1e-9, seed=0,
           replay=None, sample_times=None, hist=None, hist_bins=0, precision="fp64",
           device=0, max_attempts=0, max_records=0, no_records=False, tstop_policy=0,
-          ref_quirks=False, xc0=None, xd0=None, xd_transport="int64", save_c_count=0, save_d_count=0):
+          ref_quirks=False, xc0=None, xd0=None, xd_transport="int64", save_c_count=0, save_d_count=0,
+          devices=None, save_rate=False, ind_save_c=None, ind_save_d=None):
     """Returns (desc, opts, keepalive).  `info` is the model's pdmp_model_info.
 
     xc0 / xd0 override the problem's (broadcast) initial conditions with per-trajectory
@@ -29,7 +30,11 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
     hist: list of (component, lo, hi).
     xd_transport: "int64" (reference layout), "int32" (always exact), "int16", or "auto" = the
     narrowest width that provably holds |xd0| + (n_jumps - 1) max|nu| (int32 when the model has a
-    Delta, which may move xd arbitrarily)."""
+    Delta, which may move xd arbitrarily).
+    devices: list of CUDA ordinals; the ensemble is sharded over them inside the library call.
+    save_rate: also return the total rate at every saved jump (reference `save_rate` / PDMPResult.rates).
+    ind_save_c / ind_save_d: 0-based indices of the continuous / discrete components to save (the
+    reference's 1-based `ind_save_c` / `ind_save_d`, src/chv.jl:54-62); None saves all."""
     if n_jumps is None or not np.isfinite(n_jumps):
         raise ValueError("n_jumps must be given and finite for an ensemble solve (the reference "
                          "default Inf64 has no meaning with heavy-tailed jump counts)")
@@ -63,9 +68,9 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
     d.nu_col_major = 0
     d.n_parms = parms.size
     kind = getattr(problem.R, "rate_kind", 0)     # rate.py wrappers; a bare R is a VariableRate (src/problem.jl:55)
-    if kind == 2:
-        raise NotImplementedError("CompositeRate needs a device functor split into a constant and a variable part; "
-                                  "use ConstantRate (rates depending on xd only) or the plain functor")
+    if kind == 2 and not info.composite:
+        raise ValueError(f"CompositeRate: device model '{info.name.decode()}' is not registered with a constant + variable "
+                         "split of its total rate (csrc/models.cuh: COMPOSITE_OK, rtot_cst, rtot_var)")
     d.rate_kind = kind
 
     o = _abi.SolveOpts()
@@ -115,6 +120,23 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
         raise ValueError("xd_transport='int16' is not provably exact for this problem (bound %d)" % bound)
     o.xd_bytes = {"int64": 8, "int32": 4, "int16": 2}[xd_transport]
     o.save_c_count, o.save_d_count = int(save_c_count), int(save_d_count)
+    if devices is not None:
+        dv = np.ascontiguousarray(devices, dtype=np.int32).reshape(-1)
+        if dv.size == 0:
+            raise ValueError("devices must not be empty")
+        keep.append(dv)
+        o.devices, o.n_devices = _ptr(dv, C.c_int32), dv.size
+        o.device = int(dv[0])
+    o.save_rate = int(bool(save_rate))
+
+    def mask(ind, n, what):
+        if ind is None:
+            return 0
+        ind = sorted(set(int(i) for i in ind))
+        if not ind or ind[0] < 0 or ind[-1] >= n:
+            raise ValueError(f"{what} must be indices in [0, {n})")
+        return sum(1 << i for i in ind)
+    o.save_c_mask, o.save_d_mask = mask(ind_save_c, info.n_c, "ind_save_c"), mask(ind_save_d, info.n_d, "ind_save_d")
     return d, o, keep
 
 
@@ -132,6 +154,8 @@ def _arr(ptr, shape, dtype, copy):
 
 def to_numpy(res, *, copy=True, save_positions=(False, True), sample_times=None, keep=None,
              records=True):
+    if int(res.n_blocks) > 1:
+        return _from_blocks(res, copy=copy, save_positions=save_positions, sample_times=sample_times, keep=keep, records=records)
     n, tot = int(res.n_traj), int(res.total_records) if records else 0
     T, Cc, H, B = res.n_sample_times, res.n_comp, res.hist_n, res.hist_bins
     nc, nd = res.n_c, res.n_d
@@ -148,6 +172,7 @@ def to_numpy(res, *, copy=True, save_positions=(False, True), sample_times=None,
         stat_sum=_arr(res.stat_sum, (T, Cc), np.float64, copy),
         stat_sumsq=_arr(res.stat_sumsq, (T, Cc), np.float64, copy),
         hist=_arr(res.hist, (T, H, B), np.uint64, copy),
+        rate=_arr(res.rate, (tot,), np.float64, copy) if res.rate else None,
         counters=dict(rk_attempts=int(res.rk_attempts), rk_rejects=int(res.rk_rejects),
                       aux_attempts=int(res.aux_attempts), total_jumps=int(res.total_jumps),
                       total_candidates=int(res.total_candidates), kernel_ms=float(res.kernel_ms),
@@ -158,4 +183,33 @@ def to_numpy(res, *, copy=True, save_positions=(False, True), sample_times=None,
         sample_times=None if sample_times is None else np.array(sample_times, dtype=np.float64),
         _keep=keep,
     )
+    return out
+
+
+def _from_blocks(res, *, copy, save_positions, sample_times, keep, records):
+    """Multi-device result: one block per device shard (include/pdmp_b200.h, pdmp_result.blocks).  The blocks
+    stay separate views (`out.blocks`); the flat arrays of the EnsembleResult are their concatenation
+    (a host copy), with the offsets rebased, so that `res[i]` and the whole-array properties work unchanged."""
+    blocks = [to_numpy(res.blocks[g], copy=copy, save_positions=save_positions, sample_times=sample_times, keep=keep,
+                       records=records) for g in range(int(res.n_blocks))]
+    for g, b in enumerate(blocks):
+        b.shard = (int(res.blocks[g].traj_begin), b.n_traj)
+        b.device = int(res.blocks[g].device)
+    T, Cc, H, B = res.n_sample_times, res.n_comp, res.hist_n, res.hist_bins
+    base = np.cumsum([0] + [len(b.time) for b in blocks])
+    offsets = np.concatenate([b.offsets[:-1] + np.uint64(base[g]) for g, b in enumerate(blocks)] + [np.array([base[-1]], np.uint64)])
+    cat = lambda name: np.concatenate([getattr(b, name) for b in blocks])
+    out = EnsembleResult(
+        n_traj=int(res.n_traj), n_c=res.n_c, n_d=res.n_d, offsets=offsets, time=cat("time"), xc=cat("xc"), xd=cat("xd"),
+        njumps=cat("njumps"), nrejected=cat("nrejected"), status=cat("status"),
+        stat_count=_arr(res.stat_count, (T, Cc), np.float64, True), stat_sum=_arr(res.stat_sum, (T, Cc), np.float64, True),
+        stat_sumsq=_arr(res.stat_sumsq, (T, Cc), np.float64, True), hist=_arr(res.hist, (T, H, B), np.uint64, True),
+        rate=cat("rate") if blocks[0].rate is not None else None,
+        counters=dict(rk_attempts=int(res.rk_attempts), rk_rejects=int(res.rk_rejects), aux_attempts=int(res.aux_attempts),
+                      total_jumps=int(res.total_jumps), total_candidates=int(res.total_candidates),
+                      kernel_ms=float(res.kernel_ms), compact_ms=float(res.compact_ms), h2d_ms=float(res.h2d_ms),
+                      d2h_ms=float(res.d2h_ms), total_records=int(res.total_records), records_needed=int(res.records_needed)),
+        save_positions=tuple(bool(x) for x in save_positions),
+        sample_times=None if sample_times is None else np.array(sample_times, dtype=np.float64), _keep=keep)
+    out.blocks = blocks
     return out

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_scan.cuh>
@@ -23,14 +24,14 @@ namespace pdmp {
 // one translation unit per model (parallel nvcc), collected here
 ModelEntry entry_tcp(int), entry_tcp2d(int), entry_morris_lecar(int), entry_sir_rejection(int), entry_sir(int),
     entry_pdmp_stiff(int), entry_tcp_rejection(int), entry_pdmp_explosion(int), entry_neuron_eva(int),
-    entry_pdmp_stiff_delta(int), entry_rates_cst(int);
+    entry_pdmp_stiff_delta(int), entry_rates_cst(int), entry_rates_composite(int);
 
 static const std::vector<ModelEntry>& registry() {
     static const std::vector<ModelEntry> r = {
         entry_tcp(0),           entry_tcp2d(1),         entry_morris_lecar(2),
         entry_sir_rejection(3), entry_sir(4),           entry_pdmp_stiff(5),
         entry_tcp_rejection(6), entry_pdmp_explosion(7), entry_neuron_eva(8),
-        entry_pdmp_stiff_delta(9), entry_rates_cst(10)};
+        entry_pdmp_stiff_delta(9), entry_rates_cst(10), entry_rates_composite(11)};
     return r;
 }
 
@@ -163,6 +164,8 @@ struct pdmp_ensemble {
     long long* d_njumps = nullptr; long long* d_nrej = nullptr; unsigned char* d_status = nullptr;
     double* d_st_time = nullptr; double* d_st_xc = nullptr; long long* d_st_xd = nullptr;  // exact-flow path: strided records
     unsigned long long* d_offsets = nullptr; double* d_time = nullptr; double* d_xc = nullptr; unsigned char* d_xd = nullptr;
+    double* d_rate_pool[NS] = {}; double* d_rate = nullptr;   // save_rate: total rate per pool slot / per CSR record
+    int nco = 0, ndo = 0;   // saved components per point (ind_save_c / ind_save_d)
     int xb = 8;  // bytes per saved discrete component (opts.xd_bytes)
     void* d_scan[NS] = {}; size_t scan_bytes = 0;
     unsigned long long csr_cap = 0, pool_blocks = 0;
@@ -174,7 +177,7 @@ struct pdmp_ensemble {
     std::vector<cudaEvent_t> ev_base, ev_done, ev_c0, ev_c1;
     // host staging (pinned)
     Pinned<unsigned long long> h_offsets, h_hist, h_ctl, h_bound, h_blk;
-    Pinned<double> h_time, h_xc, h_stats;
+    Pinned<double> h_time, h_xc, h_stats, h_rate;
     Pinned<long long> h_njumps, h_nrej;
     Pinned<unsigned char> h_xd;
     Pinned<unsigned char> h_status;
@@ -182,14 +185,21 @@ struct pdmp_ensemble {
     float ms_kernel = 0, ms_compact = 0;
     double ms_h2d = 0, ms_d2h = 0;
     cudaStream_t last_stream = nullptr;
+    // multi-device parent (opts.n_devices > 1): owns one complete ensemble per device shard and nothing else
+    std::vector<pdmp_ensemble*> shards;
+    std::vector<unsigned long long> shard_begin;       // [n_shards + 1] global trajectory ranges
+    std::vector<pdmp_result> blocks;                   // per-shard results of the last run / fetch
+    std::vector<double> sum_stats; std::vector<unsigned long long> sum_hist;   // statistics summed over the shards
 
     ~pdmp_ensemble() {
+        if (!shards.empty()) { for (auto* sh : shards) delete sh; return; }
         cudaSetDevice(device);
         cudaDeviceSynchronize();
         void* bufs[] = {d_xc0, d_xd0, d_replay, d_sample, d_stats, d_hist, d_ctl, d_blkhist, d_segtab,
                         d_nrec, d_njumps, d_nrej, d_status, d_offsets, d_time, d_xc, d_xd, d_st_time, d_st_xc, d_st_xd};
         for (void* b : bufs) if (b) cudaFree(b);
-        for (int q = 0; q < NS; ++q) { if (d_pool[q]) cudaFree(d_pool[q]); if (d_scan[q]) cudaFree(d_scan[q]); }
+        for (int q = 0; q < NS; ++q) { if (d_pool[q]) cudaFree(d_pool[q]); if (d_scan[q]) cudaFree(d_scan[q]); if (d_rate_pool[q]) cudaFree(d_rate_pool[q]); }
+        if (d_rate) cudaFree(d_rate);
         cudaEvent_t evs[] = {ev_fork, ev_kbeg, ev_h2d[0], ev_h2d[1], ev_d2h[0], ev_d2h[1]};
         for (auto e : evs) if (e) cudaEventDestroy(e);
         for (auto e : ev_kend) if (e) cudaEventDestroy(e);
@@ -201,6 +211,107 @@ struct pdmp_ensemble {
 
 // d_ctl layout (unsigned long long): [2*s + 0] work cursor, [2*s + 1] block cursor of compute stream s; counters after
 enum { CTL_SHARED_BLK = 2 * NS, CTL_CT = 2 * NS + 1, CTL_N = 2 * NS + 1 + CT_N };
+
+// ---- multi-device: the ensemble sharded over opts.devices[], one host thread per device --------------------
+// (contiguous global id ranges, no data-path exchange; the statistics — KBs — are summed on
+//  the host in block order, so the sums do not depend on thread timing)
+static int create_multi(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_ensemble** out) {
+    const int G = o->n_devices;
+    if (!o->devices) return fail(PDMP_ERR_INVALID, "devices is null");
+    if (G > 64) return fail(PDMP_ERR_INVALID, "at most 64 device shards");
+    const int ndev = pdmp_device_count();
+    for (int g = 0; g < G; ++g)
+        if (o->devices[g] < 0 || o->devices[g] >= ndev)
+            return fail(PDMP_ERR_NO_DEVICE, "devices[" + std::to_string(g) + "] = " + std::to_string(o->devices[g]) + " is not a usable CUDA device");
+    if (d->model_id >= (int)registry().size()) return fail(PDMP_ERR_UNSUPPORTED, "exact-flow models run on one device per call");
+    if (d->model_id < 0) return fail(PDMP_ERR_MODEL, "unknown model id");
+    const ModelEntry& m = registry()[d->model_id];
+    const int NC = m.info.n_c, ND = m.info.n_d;
+    auto* parent = new pdmp_ensemble();
+    std::unique_ptr<pdmp_ensemble> guard(parent);
+    parent->device = o->devices[0]; parent->m = &m; parent->o = *o; parent->n = d->n_traj;
+    parent->shards.assign(G, nullptr);
+    parent->shard_begin.resize(G + 1);
+    for (int g = 0; g <= G; ++g) parent->shard_begin[g] = (unsigned long long)(((unsigned __int128)d->n_traj * g) / G);
+    std::vector<int> rcs(G, PDMP_OK);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g)
+        th.emplace_back([&, g] {
+            const unsigned long long a = parent->shard_begin[g], cnt = parent->shard_begin[g + 1] - a;
+            pdmp_problem_desc dg = *d;
+            pdmp_solve_opts og = *o;
+            dg.n_traj = cnt; dg.traj_id_offset = d->traj_id_offset + a;
+            if (d->xc0_per_traj && d->xc0) dg.xc0 = d->xc0 + a * NC;
+            if (d->xd0_per_traj && d->xd0) dg.xd0 = d->xd0 + a * ND;
+            if (o->replay_u) og.replay_u = o->replay_u + a * o->replay_stride;
+            og.device = o->devices[g]; og.devices = nullptr; og.n_devices = 0;
+            if (o->max_records && d->n_traj)   // the caller's capacity, split by shard size with 10 % slack for imbalance
+                og.max_records = (unsigned long long)std::ceil(1.1 * (double)o->max_records * (double)cnt / (double)d->n_traj) + 1024;
+            rcs[g] = pdmp_ensemble_create(&dg, &og, &parent->shards[g]);
+            if (rcs[g]) errs[g] = pdmp_last_error();
+        });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rcs[g]) return fail(rcs[g], "device shard " + std::to_string(g) + " (device " + std::to_string(o->devices[g]) + "): " + errs[g]);
+    parent->nco = parent->shards[0]->nco; parent->ndo = parent->shards[0]->ndo; parent->xb = parent->shards[0]->xb;
+    *out = guard.release();
+    return PDMP_OK;
+}
+
+// sums the per-shard results into the parent's result: counters and statistics added in block order
+static int aggregate_blocks(pdmp_ensemble* e, pdmp_result* r, const std::vector<int>& rcs, const std::vector<std::string>& errs) {
+    const int G = (int)e->shards.size();
+    int rc = PDMP_OK;
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] && rcs[g] != PDMP_ERR_CAPACITY)
+            return fail(rcs[g], "device shard " + std::to_string(g) + " (device " + std::to_string(e->shards[g]->device) + "): " + errs[g]);
+    std::memset(r, 0, sizeof(*r));
+    const pdmp_result& b0 = e->blocks[0];
+    const size_t ns = (size_t)b0.n_sample_times * b0.n_comp, nh = (size_t)b0.n_sample_times * b0.hist_n * b0.hist_bins;
+    e->sum_stats.assign(3 * ns, 0.0); e->sum_hist.assign(nh, 0ull);
+    for (int g = 0; g < G; ++g) {
+        pdmp_result& b = e->blocks[g];
+        b.traj_begin = e->shard_begin[g]; b.device = e->shards[g]->device; b.owner = nullptr; b.blocks = nullptr; b.n_blocks = 0;
+        r->n_traj += b.n_traj; r->total_records += b.total_records; r->records_needed += b.records_needed;
+        r->rk_attempts += b.rk_attempts; r->rk_rejects += b.rk_rejects; r->aux_attempts += b.aux_attempts;
+        r->total_jumps += b.total_jumps; r->total_candidates += b.total_candidates;
+        r->kernel_ms = std::max(r->kernel_ms, b.kernel_ms); r->compact_ms = std::max(r->compact_ms, b.compact_ms);
+        r->h2d_ms = std::max(r->h2d_ms, b.h2d_ms); r->d2h_ms = std::max(r->d2h_ms, b.d2h_ms);
+        if (b.stat_count) for (size_t i = 0; i < ns; ++i) {
+            e->sum_stats[i] += b.stat_count[i]; e->sum_stats[ns + i] += b.stat_sum[i]; e->sum_stats[2 * ns + i] += b.stat_sumsq[i];
+        }
+        if (b.hist) for (size_t i = 0; i < nh; ++i) e->sum_hist[i] += b.hist[i];
+        if (rcs[g] == PDMP_ERR_CAPACITY) rc = PDMP_ERR_CAPACITY;
+    }
+    r->n_sample_times = b0.n_sample_times; r->n_comp = b0.n_comp; r->hist_n = b0.hist_n; r->hist_bins = b0.hist_bins;
+    r->n_c = b0.n_c; r->n_d = b0.n_d; r->xd_bytes = b0.xd_bytes; r->device = e->device;
+    r->stat_count = e->sum_stats.data(); r->stat_sum = e->sum_stats.data() + ns; r->stat_sumsq = e->sum_stats.data() + 2 * ns;
+    r->hist = (uint64_t*)e->sum_hist.data();
+    r->blocks = e->blocks.data(); r->n_blocks = G;
+    if (rc == PDMP_ERR_CAPACITY)
+        return fail(rc, "record pool exhausted on at least one device shard: about " + std::to_string(r->records_needed) +
+                            " record slots needed in total; truncated trajectories carry status OUTPUT_OVERFLOW");
+    return PDMP_OK;
+}
+
+// runs f(shard index, shard, block result) on one host thread per shard and aggregates
+template <class F>
+static int for_each_shard(pdmp_ensemble* e, pdmp_result* r, F&& f) {
+    const int G = (int)e->shards.size();
+    e->blocks.assign(G, pdmp_result{});
+    std::vector<int> rcs(G, PDMP_OK);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g)
+        th.emplace_back([&, g] {
+            rcs[g] = f(g, e->shards[g], &e->blocks[g]);
+            if (rcs[g]) errs[g] = pdmp_last_error();
+        });
+    for (auto& t : th) t.join();
+    return r ? aggregate_blocks(e, r, rcs, errs) : (*std::max_element(rcs.begin(), rcs.end()) ? fail(*std::max_element(rcs.begin(), rcs.end()), errs[std::max_element(rcs.begin(), rcs.end()) - rcs.begin()]) : PDMP_OK);
+}
+
 
 extern "C" {
 
@@ -228,9 +339,16 @@ int32_t pdmp_model_lookup(const char* name, pdmp_model_info* out) {
     return fail(PDMP_ERR_MODEL, std::string("unknown model '") + name + "'");
 }
 
+
 int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_ensemble** out) {
     if (!d || !o || !out) return fail(PDMP_ERR_INVALID, "null argument");
     *out = nullptr;
+    if (o->n_devices > 1) return create_multi(d, o, out);
+    if (o->n_devices == 1 && o->devices) {   // a one-entry list names the device
+        pdmp_solve_opts o1 = *o;
+        o1.device = o->devices[0]; o1.devices = nullptr; o1.n_devices = 0;
+        return pdmp_ensemble_create(d, &o1, out);
+    }
     if (d->model_id >= (int)registry().size() && d->model_id < pdmp_model_count())
         return fail(PDMP_ERR_UNSUPPORTED, "exact-flow models run through pdmp_solve_ensemble (no resident handle)");
     if (d->model_id < 0 || d->model_id >= (int)registry().size()) return fail(PDMP_ERR_MODEL, "unknown model id");
@@ -249,7 +367,17 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
                                         std::to_string(m.info.n_parms) + " parameters");
     if (!d->xc0 || !d->xd0 || !d->nu || (!d->parms && d->n_parms)) return fail(PDMP_ERR_INVALID, "null problem array");
     if (o->algorithm != PDMP_ALG_CHV && o->algorithm != PDMP_ALG_REJECTION) return fail(PDMP_ERR_INVALID, "algorithm");
-    if (d->rate_kind != 0 && d->rate_kind != 1) return fail(PDMP_ERR_INVALID, "rate_kind");
+    if (d->rate_kind < 0 || d->rate_kind > 2) return fail(PDMP_ERR_INVALID, "rate_kind");
+    if (d->rate_kind == 2 && !m.composite_ok)
+        return fail(PDMP_ERR_UNSUPPORTED, std::string("model '") + m.info.name + "' is not registered with a constant + variable "
+                                              "split of its total rate: CompositeRate unavailable");
+    if (d->rate_kind == 2 && o->algorithm != PDMP_ALG_CHV) return fail(PDMP_ERR_UNSUPPORTED, "CompositeRate: CHV only");
+    // the reference's rejectionjump calls pushXc!/pushXd!/pushTime!, which do not exist (src/rejectiondiffeq.jl:47-49):
+    // solve(problem, Rejection(ode); save_positions = (true, _)) throws UndefVarError there
+    if (o->algorithm == PDMP_ALG_REJECTION && o->save_pre)
+        return fail(PDMP_ERR_UNSUPPORTED, "Rejection: pre-jump saving is not available (the reference throws UndefVarError: pushXc!)");
+    if ((NC < 64 && (o->save_c_mask >> NC)) || (ND < 64 && (o->save_d_mask >> ND)))
+        return fail(PDMP_ERR_INVALID, "save_c_mask / save_d_mask select components the model does not have");
     if (d->rate_kind == 1 && !m.const_rate_ok)
         return fail(PDMP_ERR_UNSUPPORTED, std::string("model '") + m.info.name + "' has rates that vary between jumps: "
                                               "ConstantRate would change its results");
@@ -270,6 +398,13 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     std::unique_ptr<pdmp_ensemble> guard(e);
     e->device = o->device; e->m = &m; e->o = *o; e->n = d->n_traj;
     e->xb = o->xd_bytes ? o->xd_bytes : 8;
+    {
+        const unsigned long long allc = NC >= 64 ? ~0ull : ((1ull << NC) - 1), alld = ND >= 64 ? ~0ull : ((1ull << ND) - 1);
+        e->P.save_c_mask = o->save_c_mask ? o->save_c_mask : allc;
+        e->P.save_d_mask = o->save_d_mask ? o->save_d_mask : alld;
+        e->nco = __builtin_popcountll(e->P.save_c_mask); e->ndo = __builtin_popcountll(e->P.save_d_mask);
+        e->P.n_c_out = e->nco; e->P.n_d_out = e->ndo;
+    }
     for (auto& st : e->cs) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
     for (cudaEvent_t* ev : {&e->ev_kbeg, &e->ev_h2d[0], &e->ev_h2d[1], &e->ev_d2h[0], &e->ev_d2h[1]}) CK(cudaEventCreate(ev));
@@ -310,6 +445,8 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     }
     P.t0 = d->t0; P.tf = d->tf;
     P.rate_const = d->rate_kind == 1;
+    P.rate_composite = d->rate_kind == 2;
+    P.ref_quirks = o->ref_quirks != 0;
     P.reltol = o->reltol; P.abstol = o->abstol;
     P.n_jumps = o->n_jumps;
     P.max_attempts = default_max_attempts(*o);
@@ -383,8 +520,8 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     if (e->records) {
         const unsigned long long maxrec = max_records_per_traj(*o);
         P.table_w = table_width(maxrec);
-        const size_t rec_bytes = (size_t)m.rec_words * 8;
-        const size_t csr_bytes = (size_t)8 * (1 + NC) + (size_t)e->xb * ND;
+        const size_t rec_bytes = (size_t)m.rec_words * 8 + (o->save_rate ? 8 : 0);
+        const size_t csr_bytes = (size_t)8 * (1 + e->nco) + (size_t)e->xb * e->ndo + (o->save_rate ? 8 : 0);
         const unsigned long long per_traj_worst = pool_records_for(maxrec);
         const unsigned long long worst = n * per_traj_worst;
         int npools = std::min(NS, e->n_chunks);
@@ -419,18 +556,22 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         if (e->shared_pool) e->csr_cap = e->pool_blocks * REC_BLOCK;
         else
             e->csr_cap = std::min<unsigned long long>(worst, e->pool_blocks * REC_BLOCK * (unsigned long long)e->n_chunks);
-        const size_t pool_bytes = (size_t)e->pool_blocks * REC_BLOCK * rec_bytes;
-        if (pool_bytes * npools + e->csr_cap * csr_bytes + fixed > free_b)
+        const size_t pool_bytes = (size_t)e->pool_blocks * REC_BLOCK * (size_t)m.rec_words * 8;
+        if ((pool_bytes + (o->save_rate ? (size_t)e->pool_blocks * REC_BLOCK * 8 : 0)) * npools + e->csr_cap * csr_bytes + fixed > free_b)
             return fail(PDMP_ERR_CAPACITY, "record pools + CSR (" +
                                                std::to_string((pool_bytes * npools + e->csr_cap * csr_bytes) >> 20) +
                                                " MiB) exceed free device memory; lower max_records or shard the ensemble");
         for (int q = 0; q < npools; ++q) CK(cudaMalloc(&e->d_pool[q], std::max<size_t>(pool_bytes, 16)));
+        if (o->save_rate) {
+            for (int q = 0; q < npools; ++q) CK(cudaMalloc(&e->d_rate_pool[q], std::max<size_t>((size_t)e->pool_blocks * REC_BLOCK, 1) * sizeof(double)));
+            CK(cudaMalloc(&e->d_rate, std::max<size_t>(e->csr_cap, 1) * sizeof(double)));
+        }
         CK(cudaMalloc(&e->d_segtab, std::max<size_t>((size_t)n * P.table_w, 1) * sizeof(unsigned)));
         CK(cudaMalloc(&e->d_offsets, (n + 1) * sizeof(unsigned long long)));
         CK(cudaMemsetAsync(e->d_offsets, 0, sizeof(unsigned long long), s0));
         CK(cudaMalloc(&e->d_time, std::max<size_t>(e->csr_cap, 1) * sizeof(double)));
-        CK(cudaMalloc(&e->d_xc, std::max<size_t>(e->csr_cap * NC, 1) * sizeof(double)));
-        CK(cudaMalloc(&e->d_xd, std::max<size_t>(e->csr_cap * ND, 1) * e->xb));
+        CK(cudaMalloc(&e->d_xc, std::max<size_t>(e->csr_cap * e->nco, 1) * sizeof(double)));
+        CK(cudaMalloc(&e->d_xd, std::max<size_t>(e->csr_cap * e->ndo, 1) * e->xb));
         P.seg_table = e->d_segtab; P.pool_blocks = e->pool_blocks;
         CK(cub::DeviceScan::ExclusiveScan(nullptr, e->scan_bytes, e->d_nrec, e->d_offsets, AddULL(),
                                           cub::FutureValue<unsigned long long>(e->d_offsets), (long long)n, s0));
@@ -484,6 +625,14 @@ static int upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc0_per_traj,
 int32_t pdmp_ensemble_upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc0_per_traj, const int64_t* xd0,
                                  int32_t xd0_per_traj) {
     if (!e) return fail(PDMP_ERR_INVALID, "null ensemble");
+    if (!e->shards.empty()) {
+        const int NC = e->m->info.n_c, ND = e->m->info.n_d;
+        return for_each_shard(e, nullptr, [&](int g, pdmp_ensemble* sh, pdmp_result*) {
+            const unsigned long long a = e->shard_begin[g];
+            return pdmp_ensemble_upload_ics(sh, xc0 ? xc0 + (xc0_per_traj ? a * NC : 0) : nullptr, xc0_per_traj,
+                                            xd0 ? xd0 + (xd0_per_traj ? a * ND : 0) : nullptr, xd0_per_traj);
+        });
+    }
     CK(cudaSetDevice(e->device));
     int rc = upload_ics(e, xc0, xc0_per_traj, xd0, xd0_per_traj, e->cs[0]);
     if (rc) return rc;
@@ -494,7 +643,7 @@ int32_t pdmp_ensemble_upload_ics(pdmp_ensemble* e, const double* xc0, int32_t xc
 // D2H of chunk k's slice of every per-trajectory and per-record array (host mode)
 static int queue_chunk_d2h(pdmp_ensemble* e, int k, bool fetch_records) {
     const unsigned long long a = e->cur_bounds[k], b = e->cur_bounds[k + 1];
-    const int NC = e->m->info.n_c, ND = e->m->info.n_d;
+    const int NC = e->nco, ND = e->ndo;   // saved components per point
     CK(cudaEventSynchronize(e->ev_done[k]));  // chunk compacted; its record range is now known on the host
     cudaStream_t st = e->copy;
     CK(cudaStreamWaitEvent(st, e->ev_done[k], 0));
@@ -508,6 +657,7 @@ static int queue_chunk_d2h(pdmp_ensemble* e, int k, bool fetch_records) {
             CK(cudaMemcpyAsync(e->h_time.p + r0, e->d_time + r0, (r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(e->h_xc.p + r0 * NC, e->d_xc + r0 * NC, (r1 - r0) * NC * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(e->h_xd.p + r0 * ND * e->xb, e->d_xd + r0 * ND * e->xb, (r1 - r0) * ND * e->xb, cudaMemcpyDeviceToHost, st));
+            if (e->d_rate) CK(cudaMemcpyAsync(e->h_rate.p + r0, e->d_rate + r0, (r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, st));
         }
     }
     return PDMP_OK;
@@ -525,7 +675,8 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
         CK(e->h_njumps.reserve(e->n)); CK(e->h_nrej.reserve(e->n)); CK(e->h_status.reserve(e->n));
         if (fetch_records && e->records) {
             CK(e->h_offsets.reserve(e->n + 1)); CK(e->h_time.reserve_exact(e->csr_cap));
-            CK(e->h_xc.reserve_exact(e->csr_cap * NC)); CK(e->h_xd.reserve_exact(e->csr_cap * ND * e->xb));
+            CK(e->h_xc.reserve_exact(e->csr_cap * e->nco)); CK(e->h_xd.reserve_exact(e->csr_cap * e->ndo * e->xb));
+            if (e->d_rate) CK(e->h_rate.reserve_exact(e->csr_cap));
         }
     }
     CK(e->h_bound.reserve(e->n_chunks + 1)); CK(e->h_blk.reserve(e->n_chunks)); CK(e->h_ctl.reserve(CTL_N));
@@ -561,6 +712,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
         Pk.cursor = e->d_ctl + 2 * q;
         Pk.blk_cursor = e->shared_pool ? e->d_ctl + CTL_SHARED_BLK : e->d_ctl + 2 * q + 1;
         Pk.pool = e->d_pool[e->shared_pool ? 0 : q];
+        Pk.rate_pool = e->d_rate_pool[e->shared_pool ? 0 : q];
         Pk.seg_table = e->d_segtab ? e->d_segtab + a * Pk.table_w : nullptr;
         Pk.nrec += a; Pk.njumps += a; Pk.nrejected += a; Pk.status += a;
         if (k >= NS) CK(cudaMemsetAsync(e->d_ctl + 2 * q, 0, 2 * sizeof(unsigned long long), st));
@@ -576,7 +728,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
             chunk_close_kernel<<<1, 32, 0, st>>>(e->d_nrec + a, e->d_offsets + a, b - a, Pk.blk_cursor, e->d_blkhist + k);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e->ev_base[k], st));
-            CK(e->m->compact(Pk, e->d_offsets + a, e->d_time, e->d_xc, e->d_xd, e->xb, nch > 1, st));
+            CK(e->m->compact(Pk, e->d_offsets + a, e->d_time, e->d_xc, e->d_xd, e->d_rate, e->xb, nch > 1, st));
             CK(cudaMemcpyAsync(e->h_bound.p + k + 1, e->d_offsets + b, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         } else {
             chunk_close_kernel<<<1, 32, 0, st>>>(nullptr, nullptr, 0, Pk.blk_cursor, e->d_blkhist + k);
@@ -597,6 +749,13 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
 
 int32_t pdmp_ensemble_run(pdmp_ensemble* e, uint64_t seed, void* stream) {
     if (!e) return fail(PDMP_ERR_INVALID, "null ensemble");
+    if (!e->shards.empty()) {
+        // every shard on its own device and stream; the launches are asynchronous, so one host thread queues them all
+        if (stream) return fail(PDMP_ERR_UNSUPPORTED, "a multi-device run is ordered on the shards' own streams: pass stream = NULL");
+        for (auto* sh : e->shards) { int rc = pdmp_ensemble_run(sh, seed, nullptr); if (rc) return rc; }
+        e->ran = true;
+        return PDMP_OK;
+    }
     CK(cudaSetDevice(e->device));
     return run_pipeline(e, seed, (cudaStream_t)stream, false, false);
 }
@@ -628,7 +787,7 @@ static int fill_counters(pdmp_ensemble* e, pdmp_result* r) {
     r->total_candidates = e->h_ctl.p[CTL_CT + CT_CANDS];
     r->kernel_ms = e->ms_kernel; r->compact_ms = e->ms_compact;
     r->n_sample_times = e->P.n_sample; r->n_comp = e->P.n_comp; r->hist_n = e->P.hist_n; r->hist_bins = e->P.hist_bins;
-    r->n_c = e->m->info.n_c; r->n_d = e->m->info.n_d; r->xd_bytes = e->xb;
+    r->n_c = e->nco; r->n_d = e->ndo; r->xd_bytes = e->xb; r->device = e->device;
     if (e->records && e->n) {
         unsigned long long total = 0;
         CK(cudaMemcpy(&total, e->d_offsets + e->n, sizeof(total), cudaMemcpyDeviceToHost));
@@ -652,6 +811,8 @@ static bool pool_overflowed(pdmp_ensemble* e) {
 int32_t pdmp_ensemble_counters(pdmp_ensemble* e, pdmp_result* r) {
     if (!e || !r) return fail(PDMP_ERR_INVALID, "null argument");
     if (!e->ran) return fail(PDMP_ERR_INVALID, "ensemble has not run");
+    if (!e->shards.empty())
+        return for_each_shard(e, r, [&](int, pdmp_ensemble* sh, pdmp_result* b) { return pdmp_ensemble_counters(sh, b); });
     CK(cudaSetDevice(e->device));
     return fill_counters(e, r);
 }
@@ -665,6 +826,7 @@ static int fill_views(pdmp_ensemble* e, bool recs, pdmp_result* r) {
     r->hist = (uint64_t*)e->h_hist.p;
     if (recs) {
         r->offsets = (uint64_t*)e->h_offsets.p; r->time = e->h_time.p; r->xc = e->h_xc.p; r->xd = e->h_xd.p;
+        r->rate = e->d_rate ? e->h_rate.p : nullptr;
     }
     if (pool_overflowed(e))
         return fail(PDMP_ERR_CAPACITY, "record pool exhausted: about " + std::to_string(r->records_needed) +
@@ -683,11 +845,13 @@ static int fetch_stats(pdmp_ensemble* e, cudaStream_t st) {
 int32_t pdmp_ensemble_fetch(pdmp_ensemble* e, int32_t fetch_records, pdmp_result* r) {
     if (!e || !r) return fail(PDMP_ERR_INVALID, "null argument");
     if (!e->ran) return fail(PDMP_ERR_INVALID, "ensemble has not run");
+    if (!e->shards.empty())
+        return for_each_shard(e, r, [&](int, pdmp_ensemble* sh, pdmp_result* b) { return pdmp_ensemble_fetch(sh, fetch_records, b); });
     CK(cudaSetDevice(e->device));
     int rc = fill_counters(e, r);
     if (rc) return rc;
     const size_t n = e->n;
-    const int NC = e->m->info.n_c, ND = e->m->info.n_d;
+    const int NC = e->nco, ND = e->ndo;   // saved components per point
     const bool recs = fetch_records && e->records && n;
     if (e->host_mode_done && (e->host_records || !recs)) {
         // the pipeline already streamed everything but the statistics
@@ -715,6 +879,7 @@ int32_t pdmp_ensemble_fetch(pdmp_ensemble* e, int32_t fetch_records, pdmp_result
             CK(cudaMemcpyAsync(e->h_time.p, e->d_time, total * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(e->h_xc.p, e->d_xc, total * NC * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(e->h_xd.p, e->d_xd, total * ND * e->xb, cudaMemcpyDeviceToHost, st));
+            if (e->d_rate) { CK(e->h_rate.reserve(total)); CK(cudaMemcpyAsync(e->h_rate.p, e->d_rate, total * sizeof(double), cudaMemcpyDeviceToHost, st)); }
         }
     }
     CK(cudaEventRecord(e->ev_d2h[1], st));
@@ -728,6 +893,16 @@ int32_t pdmp_ensemble_fetch(pdmp_ensemble* e, int32_t fetch_records, pdmp_result
 int32_t pdmp_ensemble_run_host(pdmp_ensemble* e, uint64_t seed, const double* xc0, int32_t xc0_per_traj, const int64_t* xd0,
                                int32_t xd0_per_traj, int32_t fetch_records, pdmp_result* r) {
     if (!e || !r) return fail(PDMP_ERR_INVALID, "null argument");
+    if (!e->shards.empty()) {
+        const int NC = e->m->info.n_c, ND = e->m->info.n_d;
+        int rc = for_each_shard(e, r, [&](int g, pdmp_ensemble* sh, pdmp_result* b) {
+            const unsigned long long a = e->shard_begin[g];
+            return pdmp_ensemble_run_host(sh, seed, xc0 ? xc0 + (xc0_per_traj ? a * NC : 0) : nullptr, xc0_per_traj,
+                                          xd0 ? xd0 + (xd0_per_traj ? a * ND : 0) : nullptr, xd0_per_traj, fetch_records, b);
+        });
+        e->ran = true;
+        return rc;
+    }
     CK(cudaSetDevice(e->device));
     CK(cudaEventRecord(e->ev_h2d[0], e->cs[0]));
     int rc = upload_ics(e, xc0, xc0_per_traj, xd0, xd0_per_traj, e->cs[0]);
@@ -743,6 +918,9 @@ int32_t pdmp_ensemble_run_host(pdmp_ensemble* e, uint64_t seed, const double* xc
 
 int32_t pdmp_ensemble_stats_device(pdmp_ensemble* e, void** stats_f64, uint64_t* n_f64, void** hist_u64, uint64_t* n_u64) {
     if (!e) return fail(PDMP_ERR_INVALID, "null ensemble");
+    if (!e->shards.empty())
+        return fail(PDMP_ERR_UNSUPPORTED, "a multi-device ensemble sums its statistics in the library (fetch / counters): "
+                                          "there is no single device buffer to reduce");
     if (stats_f64) *stats_f64 = e->d_stats;
     if (n_f64) *n_f64 = e->n_stats;
     if (hist_u64) *hist_u64 = e->d_hist;
@@ -891,7 +1069,10 @@ static int solve_exact(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdm
 int32_t pdmp_solve_ensemble(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_result* r) {
     if (!d || !o || !r) return fail(PDMP_ERR_INVALID, "null argument");
     std::memset(r, 0, sizeof(*r));
-    if (d->model_id >= (int)registry().size() && d->model_id < pdmp_model_count()) return solve_exact(d, o, r);
+    if (d->model_id >= (int)registry().size() && d->model_id < pdmp_model_count()) {
+        if (o->n_devices > 1) return fail(PDMP_ERR_UNSUPPORTED, "exact-flow models run on one device per call");
+        return solve_exact(d, o, r);
+    }
     pdmp_ensemble* e = nullptr;
     int rc = pdmp_ensemble_create(d, o, &e);
     if (rc) return rc;

@@ -73,6 +73,43 @@ PDMP_DEV float apply_sign(float h, unsigned negmask, int i) {
 }
 
 // ---------------------------------------------------------------------------------------
+// -log(u) for a uniform u in (0, 1): the exponential variate of every threshold (reference
+// `-log(rand())`, src/problem.jl:153, src/chvdiffeq.jl:71, src/rejectiondiffeq.jl:36).
+// u = 2^e m with m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.172, by the
+// odd series up to s^19 (truncation 2e-17); measured against libm: <= 4.5e-16 relative.  About 40
+// instructions against ~85 for the library log: no denormal / special-case handling on the hot path
+// (any u outside the normal range (0,1) takes the library call) and the coefficients are
+// constant-bank operands of the DFMAs instead of pairs of 32-bit immediates.
+// ---------------------------------------------------------------------------------------
+static __constant__ double c_atanh[9] = {1.0 / 3, 1.0 / 5, 1.0 / 7, 1.0 / 9, 1.0 / 11, 1.0 / 13, 1.0 / 15, 1.0 / 17, 1.0 / 19};
+static __constant__ double c_ln2[2] = {0.6931471805599453094, 2.319046813846299616e-17};
+PDMP_DEV double neg_log_unit(double u) {
+    int hi = __double2hiint(u);
+    const int lo = __double2loint(u);
+    if ((unsigned)(hi - 0x00100000) >= 0x3fe00000u) return -log(u);   // not a normal number in (0, 1)
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi >= 0x3ff6a09f) { hi -= 0x00100000; e += 1; }
+    const double m = __hiloint2double(hi, lo);
+    const double a = m - 1.0, b = m + 1.0;       // b in [1.70, 2.42)
+    double rb;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rb) : "d"(b));
+    double t = fma(-b, rb, 1.0);
+    rb = fma(rb, t, rb);
+    t = fma(-b, rb, 1.0);
+    rb = fma(rb, t, rb);
+    double s = a * rb;
+    s = fma(rb, fma(-s, b, a), s);               // one residual correction of the quotient
+    const double s2 = s * s;
+    double p = c_atanh[8];
+#pragma unroll
+    for (int k = 7; k >= 0; --k) p = fma(p, s2, c_atanh[k]);
+    const double lm = fma(s + s, s2 * p, s + s);  // 2 s + 2 s^3 P(s^2)
+    const double ef = (double)e;
+    return -fma(ef, c_ln2[0], fma(ef, c_ln2[1], lm));
+}
+
+// ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  counter = (gid_lo, gid_hi, block, 0),
 // key = (seed_lo, seed_hi).  One call yields two 52-bit uniforms in (0,1): exactly one
 // CHV jump's worth (pfsample draw + next exponential).

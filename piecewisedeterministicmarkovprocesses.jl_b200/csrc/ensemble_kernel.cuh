@@ -37,6 +37,8 @@ struct KParams {
     int nu[MAXR * MAXD];  // [r * ND + d]
     double t0, tf;
     int rate_const;   // ConstantRate: the CHV field re-uses the total rate of the post-jump state
+    int rate_composite;  // CompositeRate: the constant part is cached from jump to jump, the variable part evaluated per stage
+    int ref_quirks;   // the final point at tf the way the reference computes it (default tolerances, caract.xc at tprev)
     // options
     double reltol, abstol;
     long long n_jumps, max_attempts;
@@ -63,6 +65,9 @@ struct KParams {
     unsigned long long* blk_cursor; // blocks handed out (keeps counting past capacity)
     unsigned int* seg_table;        // [n_traj][table_w] first block of each segment
     int table_w;
+    double* rate_pool;              // save_rate: total rate per pool record slot (null: not saved)
+    unsigned long long save_c_mask, save_d_mask;   // ind_save_c / ind_save_d as bit masks (compaction only)
+    int n_c_out, n_d_out;           // saved component counts = popcount of the masks
     // per-trajectory outputs
     unsigned long long* nrec;       // [n_traj + 1], records stored per trajectory
     long long* njumps;
@@ -84,9 +89,15 @@ struct RecLayout {
 template <class M, class = void> struct ConstRateOk { static constexpr bool value = false; };
 template <class M> struct ConstRateOk<M, decltype((void)M::CONST_RATE_OK)> { static constexpr bool value = M::CONST_RATE_OK; };
 
+// models whose total rate is registered as a constant part + a variable part (reference CompositeRate)
+template <class M, class = void> struct CompositeOk { static constexpr bool value = false; };
+template <class M> struct CompositeOk<M, decltype((void)M::COMPOSITE_OK)> { static constexpr bool value = M::COMPOSITE_OK; };
+
 // models whose CHV field is a sign vector times a scalar (TCP) use the single-chain RK attempt
 template <class M, class = void> struct ChvSigned { static constexpr bool value = false; };
+#ifndef PDMP_NO_SIGNED   // (experiment switch: the generic attempt for every model)
 template <class M> struct ChvSigned<M, decltype((void)M::CHV_SIGNED_SCALAR)> { static constexpr bool value = M::CHV_SIGNED_SCALAR; };
+#endif
 
 // models whose F does not depend on (xc, t) between jumps (TCP: F = +-1): the plain-F flow is exact
 template <class M, class = void> struct ConstFlow { static constexpr bool value = false; };
@@ -110,7 +121,8 @@ struct Traj {
     R y[D];             // CHV: (xc, t) in the time-change variable s ; Rejection: xc in time t
     R k1[D];            // FSAL
     double tacc;        // SHADOW_T only: the time slot in double
-    R inv_rate;         // ConstantRate (src/rate.jl:17-40): 1 / total rate, cached from jump to jump
+    R inv_rate;         // ConstantRate (src/rate.jl:17-40): 1 / total rate, cached from jump to jump;
+                        // CompositeRate (src/rate.jl:42-69): the constant part of the total rate
     double r, tstop, h; // distance of the integration variable to the next threshold (s = tstop - r; an
                         // accepted step subtracts from it, a landing makes it exactly 0), the threshold, the
                         // proposed step.  The CHV field is autonomous in s, so s itself is never formed there.
@@ -147,6 +159,8 @@ struct Traj {
                 const R tau = x[NC];
                 R inv;
                 if constexpr (ConstRateOk<M>::value) inv = P.rate_const ? inv_rate : rcp_fast(M::rtot(x, xd, P.parms, tau));
+                else if constexpr (CompositeOk<M>::value)   // out_cst .+ out_var, src/rate.jl:65-67 (inv_rate caches out_cst)
+                    inv = rcp_fast(P.rate_composite ? inv_rate + M::rtot_var(x, xd, P.parms, tau) : M::rtot(x, xd, P.parms, tau));
                 else inv = rcp_fast(M::rtot(x, xd, P.parms, tau));
                 M::F(dx, x, xd, P.parms, tau);
 #pragma unroll
@@ -162,10 +176,14 @@ struct Traj {
     PDMP_DEV void refresh_rate(const KParams& P, double t) {
         if constexpr (ConstRateOk<M>::value && ALG == PDMP_ALG_CHV)
             if (P.rate_const) inv_rate = rcp_fast(M::rtot(y, xd, P.parms, (R)t));
+        if constexpr (CompositeOk<M>::value && ALG == PDMP_ALG_CHV)
+            if (P.rate_composite) inv_rate = M::rtot_cst(y, xd, P.parms, (R)t);   // the ConstantRate part only
     }
 
     // ---- record pool writer ----------------------------------------------------------
-    PDMP_DEV void write_record(const KParams& P, double t, const R* xc) {
+    PDMP_DEV static double no_rate() { return __longlong_as_double(0x7ff8000000000000ll); }   // NaN: no jump produced this point
+    PDMP_DEV void write_record(const KParams& P, double t, const R* xc) { write_record(P, t, xc, no_rate()); }
+    PDMP_DEV void write_record(const KParams& P, double t, const R* xc, double rate_tot) {
         if constexpr (!RECORDS) return;
         if (seg_left == 0) {
             const unsigned nrecs = seg_records(seg_k);
@@ -196,6 +214,7 @@ struct Traj {
         double2* dst = reinterpret_cast<double2*>(P.pool + wslot * RL::BYTES);
 #pragma unroll
         for (int i = 0; i < RL::WORDS / 2; ++i) __stcs(dst + i, make_double2(w[2 * i], w[2 * i + 1]));
+        if (P.rate_pool) __stcs(P.rate_pool + wslot, rate_tot);   // save_rate (reference rate_hist)
         ++wslot;
         ++nrec_stored;
     }
@@ -239,7 +258,9 @@ struct Traj {
     }
 
     // ---- plain-F flow of (x, t) to tau, either direction; adaptive, same pair, user tolerances ----
-    PDMP_DEV bool flow_F(const KParams& P, R (&x)[NC], double& t, double tau, unsigned& aux_attempts, int& fail) {
+    // quirk = true: OrdinaryDiffEq's defaults of a fresh `solve(prob, ode)` — reltol 1e-3, abstol 1e-6 and the
+    // Hairer-Norsett-Wanner initial step — as the reference's last bit does (src/chvdiffeq.jl:162-163)
+    PDMP_DEV bool flow_F(const KParams& P, R (&x)[NC], double& t, double tau, unsigned& aux_attempts, int& fail, bool quirk = false) {
         if constexpr (M::ZERO_FLOW) { t = tau; return true; }
         if (t == tau) return true;
         if constexpr (ConstFlow<M>::value) {   // F is constant between jumps: the flow is x + F (tau - t), exactly
@@ -253,17 +274,41 @@ struct Traj {
         }
         const double dir = tau > t ? 1.0 : -1.0;
         double hh = tau - t;
+        const R rtol = quirk ? R(1e-3) : (R)P.reltol, atol = quirk ? R(1e-6) : (R)P.abstol;
         PIController c2; c2.init();
         R f1[NC];
         M::F(f1, x, xd, P.parms, (R)t);
         auto rhs = [&](const R* xx, R* dx, R tt) { M::F(dx, xx, xd, P.parms, tt); };
+        if (quirk) {   // ode_determine_initdt, order 5, dtmax = the interval
+            double d0 = 0.0, d1 = 0.0, sk[NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                sk[i] = (double)atol + fabs((double)x[i]) * (double)rtol;
+                const double a = (double)x[i] / sk[i], b = (double)f1[i] / sk[i];
+                d0 = fma(a, a, d0); d1 = fma(b, b, d1);
+            }
+            d0 = sqrt(d0 * (1.0 / NC)); d1 = sqrt(d1 * (1.0 / NC));
+            double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+            dt0 = fmin(dt0, fabs(hh));
+            R u1[NC], f2[NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) u1[i] = fma((R)dt0, f1[i], x[i]);
+            M::F(f2, u1, xd, P.parms, (R)(t + dt0));
+            double d2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) { const double a = ((double)f2[i] - (double)f1[i]) / sk[i]; d2 = fma(a, a, d2); }
+            d2 = sqrt(d2 * (1.0 / NC)) / dt0;
+            const double dm = fmax(d1, d2);
+            const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) / 5.0);
+            hh = fmin(fmin(100.0 * dt0, dt1), fabs(hh));
+        }
         const unsigned budget = (unsigned)min((long long)0x7fffffff, P.max_attempts);
         while (t != tau) {
             bool clipped = false;
             double step = hh;
             if (dir * step >= dir * (tau - t)) { step = tau - t; clipped = true; }
             R xn[NC], f7[NC], inc;
-            const R e2 = rk_attempt<Tab, NC, R>(rhs, x, f1, (R)t, (R)step, xn, f7, (R)P.reltol, (R)P.abstol, inc);
+            const R e2 = rk_attempt<Tab, NC, R>(rhs, x, f1, (R)t, (R)step, xn, f7, rtol, atol, inc);
             if (++aux_attempts > budget) { fail = PDMP_ST_MAX_ATTEMPTS; return false; }
             const bool accept = e2 <= (R)NC;
             double fac;
@@ -291,7 +336,7 @@ struct Traj {
     // reference src/chvdiffeq.jl:160-168 (a fresh ODE solve there)
     PDMP_DEV bool flow_anchor_to(const KParams& P, double tau, unsigned& aux_attempts, int& fail) {
         if (!(tau > ts)) return true;
-        return flow_F(P, xs, ts, tau, aux_attempts, fail);
+        return flow_F(P, xs, ts, tau, aux_attempts, fail, P.ref_quirks != 0);
     }
 
     // ---- ensemble statistics at the fixed sample times -----------------------------------
@@ -341,7 +386,7 @@ struct Traj {
         }
 #pragma unroll
         for (int i = 0; i < ND; ++i) xd[i] = (int)P.xd0[(P.xd0_per_traj ? (size_t)idx * ND : 0) + i];
-        const double E0 = -log(draw(P, exhausted));  // tstop_extended = -log(rand())
+        const double E0 = neg_log_unit(draw(P, exhausted));  // tstop_extended = -log(rand())
         double s0;
         if constexpr (ALG == PDMP_ALG_CHV) {
             y[NC] = (R)P.t0;  // X_extended[end] = ti
@@ -420,12 +465,12 @@ struct Traj {
         int fail = PDMP_ST_OK;
         bool ex = false;
         const double tj = threshold_time();
-        if (P.save_pre && tj <= P.tf) write_record(P, tj, y);  // :41-48
         R rate[NR];
         M::rates(rate, y, xd, P.parms, (R)tj);  // :51, rates at the PRE-jump state
         R tot = rate[0];
 #pragma unroll
         for (int i = 1; i < NR; ++i) tot += rate[i];  // sum(rate), left to right
+        if (P.save_pre && tj <= P.tf) write_record(P, tj, y, (double)tot);  // :41-48
         double u_exp;
         if (tj < P.tf) {  // :52
             // a positive finite total is required where pfsample uses it; at the overshoot threshold the
@@ -460,13 +505,13 @@ struct Traj {
         }
         ++simnj;                          // :70
         {
-            const double tnew = tstop - log(u_exp);   // :71, always drawn
+            const double tnew = tstop + neg_log_unit(u_exp);   // :71, always drawn
             r = tnew - tstop;                         // s sits exactly on the old threshold
             tstop = tnew;
         }
         if (!(tlast < tj)) { finish(P, PDMP_ST_NO_PROGRESS); return true; }  // @assert :145
         tlast = tj;                       // :146
-        if (P.save_post && tj <= P.tf) write_record(P, tj, xs);  // :149-156
+        if (P.save_post && tj <= P.tf) write_record(P, tj, xs, tj < P.tf ? (double)tot : no_rate());  // :149-156
         return epilogue(P, ex, aux, fail);
     }
 
@@ -486,7 +531,7 @@ struct Traj {
         rng.next2(P.rng_mode, P.replay_u + (size_t)lid * P.replay_stride, P.replay_stride, P.traj_id_offset + lid, P.keys,
                   ex, u_acc, u_exp);
         const bool reject = u_acc < 1.0 - (double)tot / (double)bnd;         // :35
-        const double dtn = -log(u_exp) / (double)bnd;                        // :36
+        const double dtn = neg_log_unit(u_exp) / (double)bnd;                        // :36
         const bool fire = tc < P.tf && !reject;
         if (fire) {                                          // :41
             const R thr = (R)draw(P, ex) * tot;              // :55
@@ -505,15 +550,19 @@ struct Traj {
             ++nfict;                                         // :66
         }
         if (tc < P.tf) {
+            // anchor of the last bit: the state at this candidate — or, the way the reference does it
+            // (ref_quirks), caract.xc of the last ACCEPTED jump paired with the time of the last candidate
+            if (fire || !P.ref_quirks) {
 #pragma unroll
-            for (int i = 0; i < NC; ++i) xs[i] = y[i];
+                for (int i = 0; i < NC; ++i) xs[i] = y[i];
+            }
             ts = tc;
         }
         tstop = tc + dtn;                                    // :71
         r = tstop - tc;
         if (tlast >= tc) { finish(P, PDMP_ST_NO_PROGRESS); return true; }  // :121-124
         tlast = tc;
-        if (P.save_post && tc <= P.tf && !reject) write_record(P, tc, y);  // :128-138
+        if (P.save_post && tc <= P.tf && !reject) write_record(P, tc, y, (double)tot);  // :128-138
         return epilogue(P, ex, aux, fail);
     }
 };
@@ -741,7 +790,8 @@ struct ModelEntry {
     cudaError_t (*occupancy)(int alg, int ode, int prec, bool records, bool stats, size_t smem, int* blocks_per_sm);
     // compaction pool -> CSR
     cudaError_t (*compact)(const KParams& P, const unsigned long long* offsets, double* time, double* xc,
-                           void* xd, int xd_bytes, bool co_resident, cudaStream_t stream);
+                           void* xd, double* rate, int xd_bytes, bool co_resident, cudaStream_t stream);
+    int composite_ok;              // CompositeOk<M>
 };
 
 // pool -> CSR: one warp per trajectory walks its segments; reads are 16-byte vector loads of
@@ -786,6 +836,28 @@ PDMP_DEV void csr_store(const double (&w)[RecLayout<M>::WORDS], unsigned long lo
     }
 }
 
+// the same with ind_save_c / ind_save_d masks (reference src/chv.jl:54-62): only the selected components, in
+// increasing index order, nco / ndo columns per saved point
+template <class M, class XT>
+PDMP_DEV void csr_store_masked(const double (&w)[RecLayout<M>::WORDS], unsigned long long o, double* __restrict__ time,
+                               double* __restrict__ xc, XT* __restrict__ xd, unsigned long long cmask, unsigned long long dmask,
+                               int nco, int ndo) {
+    constexpr int NC = M::NC, ND = M::ND;
+    __stcs(time + o, w[0]);
+    int k = 0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+        if ((cmask >> c) & 1ull) { xc[o * nco + k] = w[1 + c]; ++k; }
+    k = 0;
+#pragma unroll
+    for (int c = 0; c < ND; ++c)
+        if ((dmask >> c) & 1ull) {
+            const double pw = w[1 + NC + c / 2];
+            xd[o * ndo + k] = (XT)((c & 1) ? __double2hiint(pw) : __double2loint(pw));
+            ++k;
+        }
+}
+
 // CO = true: the variant that shares the SMs with a running ensemble kernel (host-mode pipeline):
 // 128 threads, <= 32 registers, one group of 32 records in flight per warp.  CO = false: the
 // stand-alone variant of resident runs: two groups of 32 records in flight per warp (the kernel is
@@ -797,9 +869,10 @@ PDMP_DEV void csr_store(const double (&w)[RecLayout<M>::WORDS], unsigned long lo
 template <class M, class XT, bool CO>
 __global__ void __launch_bounds__(128, CO ? 16 : PDMP_COMPACT_CTAS) compact_kernel(const KParams P, const unsigned long long* __restrict__ offsets,
                                                                double* __restrict__ time, double* __restrict__ xc,
-                                                               XT* __restrict__ xd) {
+                                                               XT* __restrict__ xd, double* __restrict__ rate) {
     using RL = RecLayout<M>;
     constexpr int UN = CO ? 1 : PDMP_COMPACT_UNROLL;
+    const bool masked = P.n_c_out != M::NC || P.n_d_out != M::ND;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -812,6 +885,7 @@ __global__ void __launch_bounds__(128, CO ? 16 : PDMP_COMPACT_CTAS) compact_kern
         // iteration moves 32 consecutive records whatever the segment boundaries
         for (unsigned r0 = lane; r0 < n; r0 += 32 * UN) {
             double w[UN][RL::WORDS];
+            double rt[UN];
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
                 const unsigned r = r0 + 32 * u;
@@ -821,6 +895,7 @@ __global__ void __launch_bounds__(128, CO ? 16 : PDMP_COMPACT_CTAS) compact_kern
                     const unsigned k = 4u * m + (q >> (4u + m));
                     const unsigned pos = q & ((16u << m) - 1u);
                     const unsigned long long slot = (unsigned long long)__ldg(tab + k) * REC_BLOCK + pos;
+                    if (rate) rt[u] = __ldcs(P.rate_pool + slot);
                     const double2* src = reinterpret_cast<const double2*>(P.pool + slot * RL::BYTES);
 #pragma unroll
                     for (int j = 0; j < RL::WORDS / 2; ++j) {
@@ -832,7 +907,11 @@ __global__ void __launch_bounds__(128, CO ? 16 : PDMP_COMPACT_CTAS) compact_kern
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
                 const unsigned r = r0 + 32 * u;
-                if (r < n) csr_store<M, XT>(w[u], off + r, time, xc, xd);
+                if (r < n) {
+                    if (masked) csr_store_masked<M, XT>(w[u], off + r, time, xc, xd, P.save_c_mask, P.save_d_mask, P.n_c_out, P.n_d_out);
+                    else csr_store<M, XT>(w[u], off + r, time, xc, xd);
+                    if (rate) __stcs(rate + off + r, rt[u]);
+                }
             }
         }
     }
@@ -886,22 +965,22 @@ cudaError_t model_occupancy(int alg, int ode, int prec, bool records, bool stats
 }
 template <class M, class XT>
 cudaError_t compact_launch(bool co_resident, const KParams& P, const unsigned long long* offsets, double* time, double* xc,
-                           XT* xd, int sms, cudaStream_t st) {
+                           XT* xd, double* rate, int sms, cudaStream_t st) {
     const unsigned long long want = (P.n_traj + 3) / 4;  // 4 warps per CTA, one trajectory per warp at a time
     const int grid = (int)std::min<unsigned long long>(want ? want : 1, (unsigned long long)sms * (co_resident ? 16 : PDMP_COMPACT_CTAS));
-    if (co_resident) compact_kernel<M, XT, true><<<grid, 128, 0, st>>>(P, offsets, time, xc, xd);
-    else compact_kernel<M, XT, false><<<grid, 128, 0, st>>>(P, offsets, time, xc, xd);
+    if (co_resident) compact_kernel<M, XT, true><<<grid, 128, 0, st>>>(P, offsets, time, xc, xd, rate);
+    else compact_kernel<M, XT, false><<<grid, 128, 0, st>>>(P, offsets, time, xc, xd, rate);
     return cudaGetLastError();
 }
 template <class M>
 cudaError_t model_compact(const KParams& P, const unsigned long long* offsets, double* time, double* xc,
-                          void* xd, int xd_bytes, bool co_resident, cudaStream_t st) {
+                          void* xd, double* rate, int xd_bytes, bool co_resident, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (xd_bytes == 2) return compact_launch<M, short>(co_resident, P, offsets, time, xc, (short*)xd, sms, st);
-    if (xd_bytes == 4) return compact_launch<M, int>(co_resident, P, offsets, time, xc, (int*)xd, sms, st);
-    return compact_launch<M, long long>(co_resident, P, offsets, time, xc, (long long*)xd, sms, st);
+    if (xd_bytes == 2) return compact_launch<M, short>(co_resident, P, offsets, time, xc, (short*)xd, rate, sms, st);
+    if (xd_bytes == 4) return compact_launch<M, int>(co_resident, P, offsets, time, xc, (int*)xd, rate, sms, st);
+    return compact_launch<M, long long>(co_resident, P, offsets, time, xc, (long long*)xd, rate, sms, st);
 }
 
 template <class M>
@@ -914,6 +993,8 @@ ModelEntry make_entry(int id) {
     e.rec_words = RecLayout<M>::WORDS;
     e.sched_jump = SchedDefaults<M>::jump; e.sched_refill = SchedDefaults<M>::refill;
     e.const_rate_ok = ConstRateOk<M>::value;
+    e.composite_ok = CompositeOk<M>::value;
+    e.info.composite = CompositeOk<M>::value;
     e.launch = &model_launch<M>;
     e.occupancy = &model_occupancy<M>;
     e.compact = &model_compact<M>;

@@ -166,6 +166,27 @@ struct RatesCstDev {  // test/testRatesCst.jl:5-24: the flow of pdmp_stiff, rate
     template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
 };
 
+struct RatesCompositeDev {  // test/testRatesComposite.jl:5-45: the flow of pdmp_stiff; rate 1 = 10 + xc[1] varies
+    static constexpr int NC = 1, ND = 2, NR = 2, NP = 1;   // between jumps (Rvar!), rate 2 = xd[2] does not (Rcst!)
+    static constexpr bool HAS_BOUND = false, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;
+    static constexpr bool COMPOSITE_OK = true;     // usable with CompositeRate (src/rate.jl:42-69)
+    static constexpr const char* NAME = "rates_composite";
+    template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
+        dx[0] = (xd[0] & 1) ? R(-3) * (x[0] * x[0]) : R(10) * x[0];
+    }
+    // R!(rate, xc, xd, parms, t, true) = R(xc[1]) + xd[2]
+    template <class R> PDMP_DEV static R rtot(const R* x, const int* xd, const double* p, R t) { return (R(10) + x[0]) + (R)xd[1]; }
+    // Rcst!(..., true) = xd[2] and Rvar!(..., true) = R(xc[1]); CompositeRate returns out_cst .+ out_var
+    template <class R> PDMP_DEV static R rtot_cst(const R* x, const int* xd, const double* p, R t) { return (R)xd[1]; }
+    template <class R> PDMP_DEV static R rtot_var(const R* x, const int* xd, const double* p, R t) { return R(10) + x[0]; }
+    template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
+        r[0] = R(10) + x[0];
+        r[1] = (R)xd[1];
+    }
+    template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(0); }
+    template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
+};
+
 struct TcpRejDev {  // examples/tcp_rejection.jl:5-25
     static constexpr int NC = 1, ND = 2, NR = 2, NP = 1;
     static constexpr bool HAS_BOUND = true, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;

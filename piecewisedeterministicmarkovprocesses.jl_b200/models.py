@@ -39,6 +39,8 @@ EXAMPLES = {
     "pdmp_stiff_delta": dict(nu=2, xc0=[1.0], xd0=[0, 0], parms=[0.0], tspan=(0.322156, 100000.0), n_jumps=50),
     # test/testRatesCst.jl:5-33: rates 10 + xd[1] and parms[1], constant between jumps
     "rates_cst": dict(nu=[[1, 0], [0, -1]], xc0=[1.0], xd0=[0, 0], parms=[0.0], tspan=(0.0, 100000.0), n_jumps=14),
+    # test/testRatesComposite.jl:49-55: rate 1 = 10 + xc[1] (variable), rate 2 = xd[2] (constant between jumps)
+    "rates_composite": dict(nu=[[1, 0], [0, -1]], xc0=[1.0], xd0=[0, 0], parms=[0.0], tspan=(0.0, 100000.0), n_jumps=20),
     # examples/tcp_rejection.jl:67-73
     "tcp_rejection": dict(nu=[[1, 0], [0, -1]], xc0=[0.0], xd0=[0, 0], parms=[0.0], tspan=(0.0, 100000.0),
                           n_jumps=50),

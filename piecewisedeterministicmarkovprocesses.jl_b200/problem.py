@@ -97,7 +97,10 @@ class EnsembleResult:
     counters: dict = field(default_factory=dict)
     save_positions: Tuple[bool, bool] = (False, True)
     sample_times: Optional[np.ndarray] = None
-    shard: Optional[Tuple[int, int]] = None   # (global id offset, count) when produced by solve_sharded
+    shard: Optional[Tuple[int, int]] = None   # (global id offset, count) when produced by solve_sharded / a device block
+    rate: Optional[np.ndarray] = None         # [total] total rate at the jump behind every saved point (save_rate)
+    blocks: Optional[list] = None             # per-device EnsembleResults of a multi-device run
+    device: int = 0
     _keep: Any = None
 
     def __len__(self):
@@ -105,7 +108,14 @@ class EnsembleResult:
 
     def __getitem__(self, i) -> PDMPResult:
         a, b = int(self.offsets[i]), int(self.offsets[i + 1])
-        return PDMPResult(self.time[a:b], self.xc[a:b].T, self.xd[a:b].T.astype(np.int64, copy=False), np.empty(0),
+        # PDMPResult.rates (src/utils.jl:69, filled by save_rate: src/chvdiffeq.jl:54, src/rejectiondiffeq.jl:134): one
+        # entry per saved jump after the initial slot, which the reference leaves uninitialised (resize!, src/problem.jl:158)
+        rates = np.empty(0)
+        if self.rate is not None:
+            rates = self.rate[a:b]
+            if b > a and np.isnan(rates[-1]) and b - a > 1:
+                rates = rates[:-1]            # the final point at tf has no rate entry in the reference
+        return PDMPResult(self.time[a:b], self.xc[a:b].T, self.xd[a:b].T.astype(np.int64, copy=False), rates,
                           self.save_positions, int(self.njumps[i]), int(self.nrejected[i]),
                           int(self.status[i]))
 

@@ -11,8 +11,9 @@ from .algorithms import CHVGPU, RejectionGPU, _GPUAlg
 
 def _common_kwargs(alg, kw):
     kw = dict(kw)
-    for dropped in ("verbose", "save_rate"):  # accepted for signature parity, no effect
-        kw.pop(dropped, None)
+    kw.pop("verbose", None)  # accepted for signature parity, no effect
+    if alg.algorithm == "rejection":
+        kw.setdefault("save_rate", True)    # the reference's default for Rejection(ode), src/rejectiondiffeq.jl:162
     if kw.pop("finalizer", None) is not None:
         raise NotImplementedError("finalizer is a Julia closure hook (src/chvdiffeq.jl:157); not portable to the device")
     kw.setdefault("reltol", 1e-7)   # reference defaults, src/chvdiffeq.jl:216-217
@@ -26,8 +27,9 @@ def solve(problem, alg, *, trajectories=1, **kw):
 
     Keyword arguments of the reference `solve` keep their meaning (n_jumps, save_positions,
     reltol, abstol); ensemble additions: trajectories, seed, replay, sample_times, hist,
-    hist_bins, device, traj_id_offset, xc0/xd0 (per-trajectory initial conditions),
-    max_records, no_records.  Returns an EnsembleResult; `res[i]` is trajectory i as a
+    hist_bins, device, devices (list of CUDA ordinals: sharded inside the library), traj_id_offset,
+    xc0/xd0 (per-trajectory initial conditions), max_records, no_records, save_rate, ind_save_c/ind_save_d
+    (0-based component indices), ref_quirks.  Returns an EnsembleResult; `res[i]` is trajectory i as a
     PDMPResult laid out like the reference's.
     """
     if not isinstance(alg, _GPUAlg):

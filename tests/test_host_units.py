@@ -131,8 +131,17 @@ def test_marshal_transport_rate_kind_and_save_counts(P):
         d, _, _ = _marshal.build(q, info(1, 2, 2), n_jumps=5, **kw)
         assert d.rate_kind == kind
     q = P.PDMPProblem("tcp", P.CompositeRate("tcp", "tcp"), np.array(ex["nu"]), ex["xc0"], ex["xd0"], ex["parms"], (0.0, 1.0))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                                  # the tcp functor has no constant + variable split
         _marshal.build(q, info(1, 2, 2), n_jumps=5, **kw)
+    ic = info(1, 2, 2); ic.composite = 1
+    d, _, _ = _marshal.build(q, ic, n_jumps=5, **kw)
+    assert d.rate_kind == 2                                          # CompositeRate (src/rate.jl:42-69)
+    # ABI v8 options: device list, save_rate, ind_save_c / ind_save_d as bit masks
+    _, o, keep = _marshal.build(pb, info(1, 2, 2), n_jumps=5, devices=[1, 0, 1], save_rate=True, ind_save_d=[1], **kw)
+    assert (o.n_devices, o.device, o.save_rate, o.save_c_mask, o.save_d_mask) == (3, 1, 1, 0, 0b10)
+    assert [o.devices[i] for i in range(3)] == [1, 0, 1]
+    with pytest.raises(ValueError):
+        _marshal.build(pb, info(1, 2, 2), n_jumps=5, ind_save_c=[1], **kw)   # only component 0 exists
     mf = P.models.problem("neuron_mf")
     d, o, _ = _marshal.build(mf, info(100, 100, 100), algorithm="rejection_exact", trajectories=2, n_jumps=50,
                              save_c_count=2, save_d_count=3)
