@@ -568,12 +568,12 @@ struct Traj {
 };
 
 // resident CTAs per SM the kernel is compiled for: small models run 6 x 128 threads (<= 80
-// registers), those with a hand-simplified CHV field (TCP) 7 x 128 (<= 72
-// registers; measured on TCP: 6 CTAs / 80 registers 54.4 ms, 7 / 72 53.0 ms, 8 / 64 53.9 ms — the
-// extra warps pay for a few spilled words), medium ones 5 (<= 96), the larger ones 4 (<= 128
+// registers), those with a hand-simplified CHV field (TCP) 8 x 128 (<= 64 registers; measured on TCP,
+// round-2 kernel, 4 M trajectories: 6 CTAs / 80 registers 39.7 ms, 7 / 72 37.8 ms, 8 / 64 37.2 ms — the
+// extra warps pay for the spilled words), medium ones 5 (<= 96), the larger ones 4 (<= 128
 // registers; Morris-Lecar loses 10 % to spills at 96)
 #ifndef PDMP_MINB_SMALL
-#define PDMP_MINB_SMALL 7
+#define PDMP_MINB_SMALL 8
 #endif
 template <class M, int ALG, class R>
 struct MinBlocks {
