@@ -31,6 +31,8 @@ extern "C" {
 
 #define PDMP_ABI_VERSION 8
 
+#define PDMP_STAT_BATCHES 64
+
 /* ---- enumerations ------------------------------------------------------------------ */
 
 /* algorithm: reference `CHV(ode)` (src/chvdiffeq.jl:2-4) / `Rejection(ode)`
@@ -234,6 +236,16 @@ typedef struct pdmp_result {
     void* owner;               /* private                                                  */
     /* ---- ABI v8 ---- */
     double* rate;              /* [total_records] when opts.save_rate, else NULL           */
+    /* Batch statistics, for confidence intervals that assume no distribution: trajectory i belongs to
+     * batch (global id) mod PDMP_STAT_BATCHES.  Sums are SHIFTED by stat_pivot[c] (the initial condition
+     * of component c when it is common to all trajectories, else 0) so that variances do not cancel:
+     *   batch_count[b][t][c] ; batch_sum = sum (v - pivot_c) ; batch_sumsq = sum (v - pivot_c)^2
+     * stat_count / stat_sum / stat_sumsq above are the totals over the batches (un-shifted).  All sums are
+     * formed in a fixed order: two runs of the same configuration return bit-identical statistics.   */
+    double* stat_pivot;        /* [C]                                                      */
+    double* batch_count;       /* [PDMP_STAT_BATCHES][T][C]                                */
+    double* batch_sum;
+    double* batch_sumsq;
     /* Multi-device runs (opts.n_devices > 1): one block per device shard, each a complete
      * pdmp_result for trajectories [traj_begin, traj_begin + n_traj) with its own CSR arrays;
      * the top-level arrays offsets/time/xc/xd/rate/njumps/nrejected/status are then NULL, the
@@ -288,8 +300,10 @@ int32_t pdmp_ensemble_run_host(pdmp_ensemble* e, uint64_t seed, const double* xc
  * ensemble, valid until the next run/destroy).  fetch_records = 0 skips the trajectory
  * arrays (counts, status, statistics and counters only). */
 int32_t pdmp_ensemble_fetch(pdmp_ensemble* e, int32_t fetch_records, pdmp_result* result);
-/* Device pointers of the statistics buffers, for the caller's NCCL all-reduce
- * (count/sum/sumsq contiguous: 3*T*C doubles; hist: T*hist_n*hist_bins uint64). */
+/* Device pointers of the statistics buffers, for the caller's NCCL all-reduce: the batch buffer
+ * [3][PDMP_STAT_BATCHES][T][C] doubles (count | shifted sum | shifted sum of squares: additive across
+ * shards, the pivot being a property of the problem) and hist [T][hist_n][hist_bins] uint64.  A fetch after
+ * the all-reduce returns the global statistics. */
 int32_t pdmp_ensemble_stats_device(pdmp_ensemble* e, void** stats_f64, uint64_t* n_f64,
                                    void** hist_u64, uint64_t* n_u64);
 /* Work counters of the last run without fetching anything else (synchronises). */

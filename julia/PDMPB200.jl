@@ -175,6 +175,10 @@ mutable struct CResult
     reserved0::Int32
     owner::Ptr{Cvoid}
     rate::Ptr{Float64}
+    stat_pivot::Ptr{Float64}
+    batch_count::Ptr{Float64}
+    batch_sum::Ptr{Float64}
+    batch_sumsq::Ptr{Float64}
     blocks::Ptr{Cvoid}
     traj_begin::UInt64
     n_blocks::Int32

@@ -485,15 +485,20 @@ struct Shared {
     const pdmp_problem_desc* d;
     const pdmp_solve_opts* o;
     int64_t nu[MAXR][MAXD];
+    double pivot[MAXC + MAXD] = {};   // shift of the batch sums: the initial condition when common to all trajectories
     // statistics: per-thread accumulators merged at the end
     int T = 0, C = 0, H = 0, B = 0;
 };
 
+// batch = (global trajectory id) mod PDMP_STAT_BATCHES; sums shifted by a pivot per component
+// (include/pdmp_b200.h, csrc/stats_kernel.cuh): bcount / bsum / bsumsq are [64][T][C]
 struct Stats {
-    std::vector<double> count, sum, sumsq;
+    std::vector<double> count, sum, sumsq, bcount, bsum, bsumsq;
     std::vector<uint64_t> hist;
     void init(int T, int C, int H, int B) {
         count.assign((size_t)T * C, 0); sum.assign((size_t)T * C, 0); sumsq.assign((size_t)T * C, 0);
+        const size_t nb = (size_t)PDMP_STAT_BATCHES * T * C;
+        bcount.assign(nb, 0); bsum.assign(nb, 0); bsumsq.assign(nb, 0);
         hist.assign((size_t)T * H * B, 0);
     }
 };
@@ -536,14 +541,18 @@ struct Sampler {
         }
         return aux.advance_to(f, tau, max_attempts, fs);
     }
+    uint64_t gid = 0;   // global trajectory id (selects the batch)
     void accumulate(int j, const double* xc, const int64_t* xd) {
         if (!st) return;
         const int C = sh.C;
+        const size_t b = (size_t)(gid % PDMP_STAT_BATCHES);
         for (int c = 0; c < C; ++c) {
             const double v = c < M::NC ? xc[c] : (double)xd[c - M::NC];
-            st->count[(size_t)j * C + c] += 1.0;
-            st->sum[(size_t)j * C + c] += v;
-            st->sumsq[(size_t)j * C + c] += v * v;
+            const double dv = v - sh.pivot[c];
+            const size_t at = (b * sh.T + j) * C + c;
+            st->bcount[at] += 1.0;
+            st->bsum[at] += dv;
+            st->bsumsq[at] += dv * dv;
         }
         for (int h = 0; h < sh.H; ++h) {
             const int c = sh.o->hist_comp[h];
@@ -629,6 +638,7 @@ void chv_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut& out,
     it.init_dt(field, 1e9);
 
     Sampler<M> smp(sh, stats);
+    smp.gid = d.traj_id_offset + i;
     smp.restart(xc, ti, tab, o.reltol, o.abstol);
     int64_t njumps_saved = 0;
     simnj = 1;  // src/chvdiffeq.jl:136
@@ -739,6 +749,7 @@ void rejection_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut
     it.init_dt(flow, 1e9);
 
     Sampler<M> smp(sh, stats);
+    smp.gid = d.traj_id_offset + i;
     smp.restart(xc, ti, tab, o.reltol, o.abstol);
     int fs = PDMP_ST_OK;
 
@@ -810,7 +821,7 @@ void rejection_trajectory(const Shared& sh, uint64_t i, DrawStream& rng, TrajOut
 // ------------------------------------------------------------------------------------
 struct ResultOwner {
     std::vector<uint64_t> offsets;
-    std::vector<double> time, xc, rate;
+    std::vector<double> time, xc, rate, pivot;
     std::vector<int64_t> xd, njumps, nrejected;
     std::vector<uint8_t> status;
     Stats stats;
@@ -829,6 +840,8 @@ int run_ensemble(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_resu
         for (int c = 0; c < M::ND; ++c)
             sh.nu[r][c] = d->nu_col_major ? d->nu[(size_t)c * M::NR + r] : d->nu[(size_t)r * M::ND + c];
     sh.T = o->n_sample_times; sh.C = M::NC + M::ND; sh.H = o->hist_n; sh.B = o->hist_bins;
+    for (int c = 0; c < M::NC + M::ND; ++c)
+        sh.pivot[c] = c < M::NC ? (d->xc0_per_traj ? 0.0 : d->xc0[c]) : (d->xd0_per_traj ? 0.0 : (double)d->xd0[c - M::NC]);
     const uint64_t n = d->n_traj;
     auto* own = new ResultOwner();
     own->njumps.resize(n); own->nrejected.resize(n); own->status.resize(n);
@@ -920,17 +933,31 @@ int run_ensemble(const pdmp_problem_desc* d, const pdmp_solve_opts* o, pdmp_resu
     }
     for (int t = 0; t < nthreads; ++t) {
         if (tstats[t].count.empty() && sh.T * sh.C > 0) continue;
-        for (size_t k = 0; k < own->stats.count.size(); ++k) {
-            if (tstats[t].count.size() != own->stats.count.size()) break;
-            own->stats.count[k] += tstats[t].count[k];
-            own->stats.sum[k] += tstats[t].sum[k];
-            own->stats.sumsq[k] += tstats[t].sumsq[k];
-        }
+        if (tstats[t].bcount.size() == own->stats.bcount.size())
+            for (size_t k = 0; k < own->stats.bcount.size(); ++k) {
+                own->stats.bcount[k] += tstats[t].bcount[k];
+                own->stats.bsum[k] += tstats[t].bsum[k];
+                own->stats.bsumsq[k] += tstats[t].bsumsq[k];
+            }
         if (tstats[t].hist.size() == own->stats.hist.size())
             for (size_t k = 0; k < own->stats.hist.size(); ++k) own->stats.hist[k] += tstats[t].hist[k];
     }
+    {   // totals over the batches, un-shifted (the same formulas as the library: csrc/abi.cu fill_views)
+        const size_t TC = (size_t)sh.T * sh.C;
+        for (size_t i = 0; i < TC; ++i) {
+            double cnt = 0, a = 0, q = 0;
+            for (int b = 0; b < PDMP_STAT_BATCHES; ++b) { cnt += own->stats.bcount[b * TC + i]; a += own->stats.bsum[b * TC + i]; q += own->stats.bsumsq[b * TC + i]; }
+            const double p = sh.pivot[i % sh.C];
+            own->stats.count[i] = cnt; own->stats.sum[i] = a + cnt * p; own->stats.sumsq[i] = q + 2.0 * p * a + cnt * p * p;
+        }
+        own->pivot.assign(sh.pivot, sh.pivot + sh.C);
+    }
     std::memset(res, 0, sizeof(*res));
     res->n_traj = n; res->total_records = total; res->records_needed = total;
+    if (sh.T) {
+        res->stat_pivot = own->pivot.data(); res->batch_count = own->stats.bcount.data();
+        res->batch_sum = own->stats.bsum.data(); res->batch_sumsq = own->stats.bsumsq.data();
+    }
     res->offsets = own->offsets.data(); res->time = own->time.data(); res->xc = own->xc.data();
     res->xd = own->xd.data(); res->njumps = own->njumps.data(); res->nrejected = own->nrejected.data();
     res->status = own->status.data();

@@ -9,6 +9,7 @@ ABI_VERSION = 8
 
 ALG_CHV, ALG_REJECTION, ALG_REJECTION_EXACT = 0, 1, 2
 ODE_DP5, ODE_TSIT5 = 0, 1
+STAT_BATCHES = 64
 RNG_PHILOX, RNG_REPLAY = 0, 1
 PREC_FP64, PREC_FP32 = 0, 1
 
@@ -74,7 +75,9 @@ Result._fields_ = [("n_traj", C.c_uint64), ("total_records", C.c_uint64), ("reco
                 ("hist_bins", C.c_int32), ("n_c", C.c_int32), ("n_d", C.c_int32),
                 ("xd_bytes", C.c_int32), ("reserved0", C.c_int32),
                 ("owner", C.c_void_p),
-                ("rate", c_double_p), ("blocks", C.POINTER(Result)), ("traj_begin", C.c_uint64),
+                ("rate", c_double_p),
+                ("stat_pivot", c_double_p), ("batch_count", c_double_p), ("batch_sum", c_double_p), ("batch_sumsq", c_double_p),
+                ("blocks", C.POINTER(Result)), ("traj_begin", C.c_uint64),
                 ("n_blocks", C.c_int32), ("device", C.c_int32)]
 
 

@@ -173,6 +173,10 @@ def to_numpy(res, *, copy=True, save_positions=(False, True), sample_times=None,
         stat_sumsq=_arr(res.stat_sumsq, (T, Cc), np.float64, copy),
         hist=_arr(res.hist, (T, H, B), np.uint64, copy),
         rate=_arr(res.rate, (tot,), np.float64, copy) if res.rate else None,
+        stat_pivot=_arr(res.stat_pivot, (Cc,), np.float64, True) if res.batch_count else None,
+        batch_count=_arr(res.batch_count, (_abi.STAT_BATCHES, T, Cc), np.float64, copy) if res.batch_count else None,
+        batch_sum=_arr(res.batch_sum, (_abi.STAT_BATCHES, T, Cc), np.float64, copy) if res.batch_count else None,
+        batch_sumsq=_arr(res.batch_sumsq, (_abi.STAT_BATCHES, T, Cc), np.float64, copy) if res.batch_count else None,
         counters=dict(rk_attempts=int(res.rk_attempts), rk_rejects=int(res.rk_rejects),
                       aux_attempts=int(res.aux_attempts), total_jumps=int(res.total_jumps),
                       total_candidates=int(res.total_candidates), kernel_ms=float(res.kernel_ms),
@@ -205,6 +209,10 @@ def _from_blocks(res, *, copy, save_positions, sample_times, keep, records):
         stat_count=_arr(res.stat_count, (T, Cc), np.float64, True), stat_sum=_arr(res.stat_sum, (T, Cc), np.float64, True),
         stat_sumsq=_arr(res.stat_sumsq, (T, Cc), np.float64, True), hist=_arr(res.hist, (T, H, B), np.uint64, True),
         rate=cat("rate") if blocks[0].rate is not None else None,
+        stat_pivot=_arr(res.stat_pivot, (Cc,), np.float64, True) if res.batch_count else None,
+        batch_count=_arr(res.batch_count, (_abi.STAT_BATCHES, T, Cc), np.float64, True) if res.batch_count else None,
+        batch_sum=_arr(res.batch_sum, (_abi.STAT_BATCHES, T, Cc), np.float64, True) if res.batch_count else None,
+        batch_sumsq=_arr(res.batch_sumsq, (_abi.STAT_BATCHES, T, Cc), np.float64, True) if res.batch_count else None,
         counters=dict(rk_attempts=int(res.rk_attempts), rk_rejects=int(res.rk_rejects), aux_attempts=int(res.aux_attempts),
                       total_jumps=int(res.total_jumps), total_candidates=int(res.total_candidates),
                       kernel_ms=float(res.kernel_ms), compact_ms=float(res.compact_ms), h2d_ms=float(res.h2d_ms),

@@ -19,6 +19,7 @@
 
 #include "ensemble_kernel.cuh"
 #include "exact_kernel.cuh"
+#include "stats_kernel.cuh"
 
 namespace pdmp {
 // one translation unit per model (parallel nvcc), collected here
@@ -170,7 +171,13 @@ struct pdmp_ensemble {
     void* d_scan[NS] = {}; size_t scan_bytes = 0;
     unsigned long long csr_cap = 0, pool_blocks = 0;
     size_t cap_xc0 = 0, cap_xd0 = 0;  // elements allocated for the initial conditions
-    size_t n_stats = 0, n_hist = 0;
+    size_t n_stats = 0, n_hist = 0;      // batch buffer [3][64][T][C] doubles ; histogram [T][H][B]
+    double* d_samples[NS] = {};          // the rows the ensemble kernel records at the sample times, one buffer per stream
+    size_t sample_rows = 0;              // trajectories a buffer holds
+    bool stat_single_ok = true;          // buffer 0 holds the whole ensemble: a resident run can be ONE kernel
+    StatParams S{};                      // histogram spec + pivot (launch-invariant part)
+    std::vector<cudaEvent_t> ev_stat;    // chunk k's rows reduced (orders the += of the chunks)
+    std::vector<double> h_tot;           // [3][T][C] totals over the batches, un-shifted (stat_count / stat_sum / stat_sumsq)
     // events
     cudaEvent_t ev_fork = nullptr, ev_kbeg = nullptr, ev_kend[NS] = {}, ev_h2d[2] = {nullptr, nullptr},
                 ev_d2h[2] = {nullptr, nullptr};
@@ -198,12 +205,12 @@ struct pdmp_ensemble {
         void* bufs[] = {d_xc0, d_xd0, d_replay, d_sample, d_stats, d_hist, d_ctl, d_blkhist, d_segtab,
                         d_nrec, d_njumps, d_nrej, d_status, d_offsets, d_time, d_xc, d_xd, d_st_time, d_st_xc, d_st_xd};
         for (void* b : bufs) if (b) cudaFree(b);
-        for (int q = 0; q < NS; ++q) { if (d_pool[q]) cudaFree(d_pool[q]); if (d_scan[q]) cudaFree(d_scan[q]); if (d_rate_pool[q]) cudaFree(d_rate_pool[q]); }
+        for (int q = 0; q < NS; ++q) { if (d_pool[q]) cudaFree(d_pool[q]); if (d_scan[q]) cudaFree(d_scan[q]); if (d_rate_pool[q]) cudaFree(d_rate_pool[q]); if (d_samples[q]) cudaFree(d_samples[q]); }
         if (d_rate) cudaFree(d_rate);
         cudaEvent_t evs[] = {ev_fork, ev_kbeg, ev_h2d[0], ev_h2d[1], ev_d2h[0], ev_d2h[1]};
         for (auto e : evs) if (e) cudaEventDestroy(e);
         for (auto e : ev_kend) if (e) cudaEventDestroy(e);
-        for (auto* v : {&ev_base, &ev_done, &ev_c0, &ev_c1}) for (auto e : *v) if (e) cudaEventDestroy(e);
+        for (auto* v : {&ev_base, &ev_done, &ev_c0, &ev_c1, &ev_stat}) for (auto e : *v) if (e) cudaEventDestroy(e);
         for (auto st : cs) if (st) cudaStreamDestroy(st);
         if (copy) cudaStreamDestroy(copy);
     }
@@ -269,7 +276,9 @@ static int aggregate_blocks(pdmp_ensemble* e, pdmp_result* r, const std::vector<
     std::memset(r, 0, sizeof(*r));
     const pdmp_result& b0 = e->blocks[0];
     const size_t ns = (size_t)b0.n_sample_times * b0.n_comp, nh = (size_t)b0.n_sample_times * b0.hist_n * b0.hist_bins;
-    e->sum_stats.assign(3 * ns, 0.0); e->sum_hist.assign(nh, 0ull);
+    const size_t nb = (size_t)STAT_BATCHES * ns;
+    e->sum_stats.assign(3 * ns + 3 * nb, 0.0); e->sum_hist.assign(nh, 0ull);
+    double* bsum = e->sum_stats.data() + 3 * ns;
     for (int g = 0; g < G; ++g) {
         pdmp_result& b = e->blocks[g];
         b.traj_begin = e->shard_begin[g]; b.device = e->shards[g]->device; b.owner = nullptr; b.blocks = nullptr; b.n_blocks = 0;
@@ -281,6 +290,9 @@ static int aggregate_blocks(pdmp_ensemble* e, pdmp_result* r, const std::vector<
         if (b.stat_count) for (size_t i = 0; i < ns; ++i) {
             e->sum_stats[i] += b.stat_count[i]; e->sum_stats[ns + i] += b.stat_sum[i]; e->sum_stats[2 * ns + i] += b.stat_sumsq[i];
         }
+        if (b.batch_count) for (size_t i = 0; i < nb; ++i) {   // same pivot on every shard: the batch sums add up
+            bsum[i] += b.batch_count[i]; bsum[nb + i] += b.batch_sum[i]; bsum[2 * nb + i] += b.batch_sumsq[i];
+        }
         if (b.hist) for (size_t i = 0; i < nh; ++i) e->sum_hist[i] += b.hist[i];
         if (rcs[g] == PDMP_ERR_CAPACITY) rc = PDMP_ERR_CAPACITY;
     }
@@ -288,6 +300,7 @@ static int aggregate_blocks(pdmp_ensemble* e, pdmp_result* r, const std::vector<
     r->n_c = b0.n_c; r->n_d = b0.n_d; r->xd_bytes = b0.xd_bytes; r->device = e->device;
     r->stat_count = e->sum_stats.data(); r->stat_sum = e->sum_stats.data() + ns; r->stat_sumsq = e->sum_stats.data() + 2 * ns;
     r->hist = (uint64_t*)e->sum_hist.data();
+    if (b0.batch_count) { r->batch_count = bsum; r->batch_sum = bsum + nb; r->batch_sumsq = bsum + 2 * nb; r->stat_pivot = b0.stat_pivot; }
     r->blocks = e->blocks.data(); r->n_blocks = G;
     if (rc == PDMP_ERR_CAPACITY)
         return fail(rc, "record pool exhausted on at least one device shard: about " + std::to_string(r->records_needed) +
@@ -419,8 +432,9 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         e->chunk_n = n ? (n + e->n_chunks - 1) / e->n_chunks : 1;
         e->n_chunks = n ? (int)((n + e->chunk_n - 1) / e->chunk_n) : 1;
     }
-    for (auto* v : {&e->ev_base, &e->ev_done, &e->ev_c0, &e->ev_c1}) v->assign(e->n_chunks, nullptr);
+    for (auto* v : {&e->ev_base, &e->ev_done, &e->ev_c0, &e->ev_c1, &e->ev_stat}) v->assign(e->n_chunks, nullptr);
     for (int k = 0; k < e->n_chunks; ++k) {
+        CK(cudaEventCreateWithFlags(&e->ev_stat[k], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&e->ev_base[k], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
         CK(cudaEventCreate(&e->ev_c0[k])); CK(cudaEventCreate(&e->ev_c1[k]));
@@ -458,7 +472,14 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         P.jump_thresh = ej ? std::max(1, std::atoi(ej)) : m.sched_jump;
         P.refill_thresh = er ? std::max(1, std::atoi(er)) : m.sched_refill;
     }
-    P.n_sample = o->n_sample_times; P.n_comp = NC + ND; P.hist_n = o->hist_n; P.hist_bins = o->hist_n ? o->hist_bins : 0;
+    P.n_sample = o->n_sample_times; P.n_comp = NC + ND;
+    StatParams& S = e->S;
+    S.T = o->n_sample_times; S.C = NC + ND; S.H = o->hist_n; S.bins = o->hist_n ? o->hist_bins : 0;
+    if (NC + ND > STAT_MAXC) return fail(PDMP_ERR_MODEL, "too many components for the statistics kernel");
+    // pivot of the shifted sums: the initial condition when it is common to all trajectories (a property of the
+    // problem, identical on every shard and rank), else 0
+    for (int c = 0; c < NC + ND; ++c)
+        S.pivot[c] = c < NC ? (d->xc0_per_traj ? 0.0 : d->xc0[c]) : (d->xd0_per_traj ? 0.0 : (double)d->xd0[c - NC]);
     e->records = !o->no_records;
     e->stats = o->n_sample_times > 0;
 
@@ -490,21 +511,34 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         for (int h = 0; h < o->hist_n; ++h) {
             if (o->hist_comp[h] < 0 || o->hist_comp[h] >= NC + ND || !(o->hist_hi[h] > o->hist_lo[h]))
                 return fail(PDMP_ERR_INVALID, "histogram spec");
-            P.hist_comp[h] = o->hist_comp[h];
-            P.hist_lo[h] = o->hist_lo[h];
-            P.hist_scale[h] = (double)o->hist_bins / (o->hist_hi[h] - o->hist_lo[h]);
+            S.hist_comp[h] = o->hist_comp[h];
+            S.hist_lo[h] = o->hist_lo[h];
+            S.hist_scale[h] = (double)o->hist_bins / (o->hist_hi[h] - o->hist_lo[h]);
         }
+        if ((size_t)S.H * S.bins * sizeof(unsigned) > 40 * 1024) return fail(PDMP_ERR_INVALID, "hist_n * hist_bins must be <= 10240");
     } else {
-        P.hist_n = 0; P.hist_bins = 0;
+        S.H = 0; S.bins = 0;
     }
-    e->n_stats = (size_t)3 * P.n_sample * P.n_comp;
-    e->n_hist = (size_t)P.n_sample * P.hist_n * P.hist_bins;
+    e->n_stats = (size_t)3 * STAT_BATCHES * S.T * S.C;
+    e->n_hist = (size_t)S.T * S.H * S.bins;
     CK(cudaMalloc(&e->d_stats, std::max<size_t>(e->n_stats, 1) * sizeof(double)));
     CK(cudaMalloc(&e->d_hist, std::max<size_t>(e->n_hist, 1) * sizeof(unsigned long long)));
-    P.stats = e->d_stats; P.hist = e->d_hist;
-    const size_t smem_need = e->n_stats * sizeof(double) + e->n_hist * sizeof(unsigned);
-    P.stats_in_smem = e->stats && smem_need <= 40 * 1024;
-    e->smem = P.stats_in_smem ? smem_need : 0;
+    S.out = e->d_stats; S.hist = e->d_hist;
+    e->smem = 0;
+    if (e->stats) {
+        // sample rows: one buffer per chunk in flight; buffer 0 holds the whole ensemble when that is affordable,
+        // so that a resident run stays one persistent kernel
+        const size_t row_bytes = (size_t)S.T * S.C * sizeof(double);
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const int nbuf = std::min(NS, e->n_chunks);
+        e->sample_rows = e->n_chunks == 1 ? (size_t)n : (size_t)e->chunk_n;
+        e->stat_single_ok = e->n_chunks == 1 || (double)n * row_bytes < 0.45 * (double)free_b;
+        for (int q = 0; q < nbuf; ++q) {
+            const size_t rows = (q == 0 && e->stat_single_ok) ? (size_t)n : e->sample_rows;
+            CK(cudaMalloc(&e->d_samples[q], std::max<size_t>(rows * row_bytes, 8)));
+        }
+    }
 
     CK(cudaMalloc(&e->d_ctl, CTL_N * sizeof(unsigned long long)));
     CK(cudaMalloc(&e->d_blkhist, e->n_chunks * sizeof(unsigned long long)));
@@ -691,7 +725,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
     // resident runs over a shared pool are ONE persistent kernel; host-mode runs (and runs whose
     // pools are per-stream) are chunked so that compaction / D2H of chunk k overlap chunk k+1
     // (measured: chunking a resident run costs 5 % at 4 chunks and 19 % at 10 — every chunk has its own tail)
-    const int nch = (!host_mode && e->shared_pool) ? 1 : e->n_chunks;
+    const int nch = (!host_mode && e->shared_pool && e->stat_single_ok) ? 1 : e->n_chunks;
     std::vector<unsigned long long>& bounds = e->cur_bounds;
     bounds.assign(1, 0ull);
     // (also measured: an unequal 2-way split so that the compaction of the first part overlaps the second
@@ -713,12 +747,21 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
         Pk.blk_cursor = e->shared_pool ? e->d_ctl + CTL_SHARED_BLK : e->d_ctl + 2 * q + 1;
         Pk.pool = e->d_pool[e->shared_pool ? 0 : q];
         Pk.rate_pool = e->d_rate_pool[e->shared_pool ? 0 : q];
+        Pk.samples = e->d_samples[nch == 1 ? 0 : q];
         Pk.seg_table = e->d_segtab ? e->d_segtab + a * Pk.table_w : nullptr;
         Pk.nrec += a; Pk.njumps += a; Pk.nrejected += a; Pk.status += a;
         if (k >= NS) CK(cudaMemsetAsync(e->d_ctl + 2 * q, 0, 2 * sizeof(unsigned long long), st));
         const int grid = (int)std::min<unsigned long long>(e->grid, (Pk.n_traj + BLOCK - 1) / BLOCK);
         CK(e->m->launch(e->o.algorithm, e->o.ode, e->o.precision, e->records, e->stats, Pk, std::max(grid, 1), e->smem, st));
         CK(cudaEventRecord(e->ev_kend[q], st));
+        if (e->stats) {   // rows -> batch moments + histograms; the chunks add up in chunk order
+            if (k > 0) CK(cudaStreamWaitEvent(st, e->ev_stat[k - 1], 0));
+            StatParams Sk = e->S;
+            Sk.samples = Pk.samples; Sk.n = Pk.n_traj; Sk.id0 = Pk.traj_id_offset;
+            stats_reduce_kernel<<<dim3(STAT_BATCHES, Sk.T), 256, (size_t)Sk.H * Sk.bins * sizeof(unsigned), st>>>(Sk);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e->ev_stat[k], st));
+        }
         if (e->records && k > 0) CK(cudaStreamWaitEvent(st, e->ev_base[k - 1], 0));  // offsets[a] (start of this chunk) is final
         CK(cudaEventRecord(e->ev_c0[k], st));
         if (e->records) {
@@ -786,7 +829,7 @@ static int fill_counters(pdmp_ensemble* e, pdmp_result* r) {
     r->total_jumps = e->h_ctl.p[CTL_CT + CT_JUMPS];
     r->total_candidates = e->h_ctl.p[CTL_CT + CT_CANDS];
     r->kernel_ms = e->ms_kernel; r->compact_ms = e->ms_compact;
-    r->n_sample_times = e->P.n_sample; r->n_comp = e->P.n_comp; r->hist_n = e->P.hist_n; r->hist_bins = e->P.hist_bins;
+    r->n_sample_times = e->P.n_sample; r->n_comp = e->P.n_comp; r->hist_n = e->S.H; r->hist_bins = e->S.bins;
     r->n_c = e->nco; r->n_d = e->ndo; r->xd_bytes = e->xb; r->device = e->device;
     if (e->records && e->n) {
         unsigned long long total = 0;
@@ -820,9 +863,20 @@ int32_t pdmp_ensemble_counters(pdmp_ensemble* e, pdmp_result* r) {
 static int fill_views(pdmp_ensemble* e, bool recs, pdmp_result* r) {
     r->d2h_ms = e->ms_d2h; r->h2d_ms = e->ms_h2d;
     r->njumps = (int64_t*)e->h_njumps.p; r->nrejected = (int64_t*)e->h_nrej.p; r->status = e->h_status.p;
-    r->stat_count = e->h_stats.p;
-    r->stat_sum = e->h_stats.p ? e->h_stats.p + e->n_stats / 3 : nullptr;
-    r->stat_sumsq = e->h_stats.p ? e->h_stats.p + 2 * (e->n_stats / 3) : nullptr;
+    if (e->n_stats && e->h_stats.p) {
+        // totals over the batches, un-shifted: sum v = sum (v - p) + n p ; sum v^2 = sum (v - p)^2 + 2 p sum (v - p) + n p^2
+        const size_t TC = (size_t)e->S.T * e->S.C, plane = (size_t)STAT_BATCHES * TC;
+        e->h_tot.assign(3 * TC, 0.0);
+        for (size_t i = 0; i < TC; ++i) {
+            double n = 0.0, a = 0.0, q = 0.0;
+            for (int b = 0; b < STAT_BATCHES; ++b) { n += e->h_stats.p[b * TC + i]; a += e->h_stats.p[plane + b * TC + i]; q += e->h_stats.p[2 * plane + b * TC + i]; }
+            const double p = e->S.pivot[i % e->S.C];
+            e->h_tot[i] = n; e->h_tot[TC + i] = a + n * p; e->h_tot[2 * TC + i] = q + 2.0 * p * a + n * p * p;
+        }
+        r->stat_count = e->h_tot.data(); r->stat_sum = e->h_tot.data() + TC; r->stat_sumsq = e->h_tot.data() + 2 * TC;
+        r->batch_count = e->h_stats.p; r->batch_sum = e->h_stats.p + plane; r->batch_sumsq = e->h_stats.p + 2 * plane;
+        r->stat_pivot = e->S.pivot;
+    }
     r->hist = (uint64_t*)e->h_hist.p;
     if (recs) {
         r->offsets = (uint64_t*)e->h_offsets.p; r->time = e->h_time.p; r->xc = e->h_xc.p; r->xd = e->h_xd.p;

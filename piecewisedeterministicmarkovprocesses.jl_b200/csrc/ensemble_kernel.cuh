@@ -48,14 +48,12 @@ struct KParams {
     PhiloxKeys keys;                 // round keys of `seed` (philox_round_keys)
     const double* replay_u;
     unsigned long long replay_stride;
-    // sampling / statistics
-    int n_sample, n_comp, hist_n, hist_bins;
+    // sampling: the ensemble kernel only RECORDS the state at the fixed sample times, one row of C = NC + ND
+    // doubles per (trajectory, sample time); stats_reduce_kernel (stats_kernel.cuh) turns the rows into batch
+    // moments and histograms in a fixed order (reproducible sums, no atomics on the integration path)
+    int n_sample, n_comp;
     const double* sample_times;
-    int hist_comp[MAXH];
-    double hist_lo[MAXH], hist_scale[MAXH];  // bin = floor((v - lo) * scale)
-    double* stats;                  // [3][T][C] count | sum | sumsq
-    unsigned long long* hist;       // [T][H][B]
-    int stats_in_smem;
+    double* samples;                // [n_traj][T][C]; slot 0 of a row is NaN when the trajectory never got there
     // work queue + counters
     unsigned long long* cursor;
     unsigned long long* counters;   // [CT_N]
@@ -219,42 +217,14 @@ struct Traj {
         ++nrec_stored;
     }
 
-    // ---- statistics at a sample time -------------------------------------------------
-    PDMP_DEV void accumulate(const KParams& P, double* sstat, unsigned* shist, int j, const R* xc) {
+    // ---- the state at a sample time: one row of the sample buffer ------------------------------
+    PDMP_DEV void accumulate(const KParams& P, int j, const R* xc) {
         if constexpr (!STATS) return;
-        const int C = P.n_comp, TC = P.n_sample * C;
-        if (P.stats_in_smem) {
-            // the count is the same for every component: ONE native 32-bit shared atomic per sample (64-bit
-            // shared atomics are CAS loops); the slot of component 0 holds it as an integer until the flush
-            atomicAdd(reinterpret_cast<unsigned*>(sstat + j * C), 1u);
+        double* row = P.samples + ((size_t)lid * P.n_sample + j) * (NC + ND);
 #pragma unroll
-            for (int c = 0; c < NC + ND; ++c) {
-                const double v = c < NC ? (double)xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
-                atomicAdd(sstat + TC + j * C + c, v);
-                atomicAdd(sstat + 2 * TC + j * C + c, v * v);
-            }
-        } else {
+        for (int c = 0; c < NC; ++c) __stcs(row + c, (double)xc[c]);
 #pragma unroll
-            for (int c = 0; c < NC + ND; ++c) {
-                const double v = c < NC ? (double)xc[c < NC ? c : 0] : (double)xd[c >= NC ? c - NC : 0];
-                atomicAdd(P.stats + j * C + c, 1.0);
-                atomicAdd(P.stats + TC + j * C + c, v);
-                atomicAdd(P.stats + 2 * TC + j * C + c, v * v);
-            }
-        }
-        for (int hh = 0; hh < P.hist_n; ++hh) {
-            const int c = P.hist_comp[hh];
-            double v = 0.0;
-#pragma unroll
-            for (int q = 0; q < NC + ND; ++q)
-                if (q == c) v = q < NC ? (double)xc[q < NC ? q : 0] : (double)xd[q >= NC ? q - NC : 0];
-            const double fb = floor((v - P.hist_lo[hh]) * P.hist_scale[hh]);
-            int b = fb < 0.0 ? 0 : (fb >= (double)P.hist_bins ? P.hist_bins - 1 : (int)fb);
-            if (!(fb == fb)) b = 0;
-            const size_t at = ((size_t)j * P.hist_n + hh) * P.hist_bins + b;
-            if (P.stats_in_smem) atomicAdd(shist + at, 1u);
-            else atomicAdd(P.hist + at, 1ull);
-        }
+        for (int c = 0; c < ND; ++c) __stcs(row + NC + c, (double)xd[c]);
     }
 
     // ---- plain-F flow of (x, t) to tau, either direction; adaptive, same pair, user tolerances ----
@@ -354,7 +324,7 @@ struct Traj {
         if constexpr (!STATS) return false;
         return tnext <= threshold_time();   // sample times are <= tf by contract; +huge when none is left
     }
-    PDMP_DEV int pre_sample(const KParams& P, double* sstat, unsigned* shist, unsigned& aux) {
+    PDMP_DEV int pre_sample(const KParams& P, unsigned& aux) {
         int fail = PDMP_ST_OK;
         if constexpr (STATS) {
             const double tcur = threshold_time(), tlim = fmin(tcur, P.tf);
@@ -366,7 +336,7 @@ struct Traj {
             for (int i = 0; i < NC; ++i) xb[i] = y[i];
             for (int j = last - 1; j >= next_sample; --j) {      // latest first: always a short backward leg
                 if (!flow_F(P, xb, tb, __ldg(P.sample_times + j), aux, fail)) return fail;
-                accumulate(P, sstat, shist, j, xb);
+                accumulate(P, j, xb);
             }
             next_sample = last;
             tnext = last < P.n_sample ? __ldg(P.sample_times + last) : 1.7976931348623157e308;
@@ -437,6 +407,9 @@ struct Traj {
 
     PDMP_DEV void finish(const KParams& P, int st) {
         if (overflow && (st == PDMP_ST_OK || st == PDMP_ST_HIT_NJUMPS)) st = PDMP_ST_OUTPUT_OVERFLOW;
+        if constexpr (STATS)   // sample times this trajectory never reached (cap, failure): not counted
+            for (int j = next_sample; j < P.n_sample; ++j)
+                __stcs(P.samples + ((size_t)lid * P.n_sample + j) * (NC + ND), __longlong_as_double(0x7ff8000000000000ll));
         P.nrec[lid] = nrec_stored;
         P.njumps[lid] = simnj;
         P.nrejected[lid] = nfict;
@@ -597,15 +570,6 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
     using T = Traj<M, Tab, ALG, RECORDS, STATS, R>;
     constexpr int D = T::D;
     constexpr bool NO_FLOW = (ALG == PDMP_ALG_REJECTION && M::ZERO_FLOW);
-    extern __shared__ double smem[];
-    double* sstat = smem;
-    unsigned* shist = reinterpret_cast<unsigned*>(smem + 3 * P.n_sample * P.n_comp);
-    if (STATS && P.stats_in_smem) {
-        const int nd = 3 * P.n_sample * P.n_comp, nh = P.n_sample * P.hist_n * P.hist_bins;
-        for (int i = threadIdx.x; i < nd; i += BLOCK) sstat[i] = 0.0;
-        for (int i = threadIdx.x; i < nh; i += BLOCK) shist[i] = 0u;
-        __syncthreads();
-    }
 
     T tr;
     int st = LANE_DEAD;
@@ -663,7 +627,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
             if constexpr (STATS) {
                 const bool due = st == LANE_WAIT && tr.sample_due(P);
                 if (__any_sync(0xffffffffu, due)) {
-                    if (due) fc = tr.pre_sample(P, sstat, shist, c_aux);
+                    if (due) fc = tr.pre_sample(P, c_aux);
                 }
             }
             if (st == LANE_WAIT) {
@@ -759,18 +723,6 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0 && x) atomicAdd(P.counters + k, x);
-    }
-    if (STATS && P.stats_in_smem) {
-        __syncthreads();
-        const int nd = 3 * P.n_sample * P.n_comp, nh = P.n_sample * P.hist_n * P.hist_bins;
-        const int TC = P.n_sample * P.n_comp;
-        for (int i = threadIdx.x; i < nd; i += BLOCK) {
-            // counts: one integer per sample time in the slot of component 0, broadcast to all components
-            const double v = i < TC ? (double)*reinterpret_cast<const unsigned*>(sstat + (i / P.n_comp) * P.n_comp) : sstat[i];
-            if (v != 0.0) atomicAdd(P.stats + i, v);
-        }
-        for (int i = threadIdx.x; i < nh; i += BLOCK)
-            if (shist[i]) atomicAdd(P.hist + i, (unsigned long long)shist[i]);
     }
 }
 

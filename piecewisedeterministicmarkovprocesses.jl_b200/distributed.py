@@ -1,7 +1,7 @@
 """Ensemble sharding across the GPUs of one box: one process per GPU (torchrun), contiguous
 global trajectory-id ranges per rank, NO data-path collective; the only exchange is one
-all-reduce (sum) of the ensemble statistics buffers (count / sum / sumsq [T, C] doubles and the
-histogram [T, H, B] uint64 — tens of KB).  Saved trajectories stay on the rank that produced
+all-reduce (sum) of the ensemble statistics buffers (batch count / shifted sum / shifted sum of squares
+[3, 64, T, C] doubles and the histogram [T, H, B] uint64 — tens of KB).  Saved trajectories stay on the rank that produced
 them.  Philox counters use the GLOBAL trajectory id, so the union of the shards is identical
 to a single-device run whatever the number of ranks (reference analogue: none — the reference
 is single-task).
@@ -40,7 +40,10 @@ def allreduce_stats_host(res, group=None):
         return res
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    f = torch.from_numpy(np.concatenate([res.stat_count.ravel(), res.stat_sum.ravel(), res.stat_sumsq.ravel()])).to(dev)
+    parts = [res.stat_count, res.stat_sum, res.stat_sumsq]
+    if res.batch_count is not None:      # the shifted batch sums add up too: the pivot is the same on every rank
+        parts += [res.batch_count, res.batch_sum, res.batch_sumsq]
+    f = torch.from_numpy(np.concatenate([a.ravel() for a in parts])).to(dev)
     h = torch.from_numpy(res.hist.astype(np.int64).ravel()).to(dev)
     if f.numel():
         dist.all_reduce(f, group=group)
@@ -50,7 +53,12 @@ def allreduce_stats_host(res, group=None):
     n = res.stat_count.size
     res.stat_count = f[:n].reshape(res.stat_count.shape)
     res.stat_sum = f[n:2 * n].reshape(res.stat_sum.shape)
-    res.stat_sumsq = f[2 * n:].reshape(res.stat_sumsq.shape)
+    res.stat_sumsq = f[2 * n:3 * n].reshape(res.stat_sumsq.shape)
+    if res.batch_count is not None:
+        m = res.batch_count.size
+        res.batch_count = f[3 * n:3 * n + m].reshape(res.batch_count.shape)
+        res.batch_sum = f[3 * n + m:3 * n + 2 * m].reshape(res.batch_sum.shape)
+        res.batch_sumsq = f[3 * n + 2 * m:].reshape(res.batch_sumsq.shape)
     res.hist = h.cpu().numpy().astype(np.uint64).reshape(res.hist.shape)
     return res
 
@@ -63,7 +71,7 @@ class _DevView:
 
 
 def stats_tensors(ens, device):
-    """(float64 tensor [3*T*C], int64 tensor [T*H*B]) aliasing the ensemble's device statistics."""
+    """(float64 tensor [3*64*T*C], int64 tensor [T*H*B]) aliasing the ensemble's device statistics."""
     import torch
     pf, nf, ph, nh = ens.stats_device()
     f = torch.as_tensor(_DevView(pf, nf, "<f8"), device=device) if nf else None

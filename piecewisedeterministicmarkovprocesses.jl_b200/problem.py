@@ -99,6 +99,11 @@ class EnsembleResult:
     sample_times: Optional[np.ndarray] = None
     shard: Optional[Tuple[int, int]] = None   # (global id offset, count) when produced by solve_sharded / a device block
     rate: Optional[np.ndarray] = None         # [total] total rate at the jump behind every saved point (save_rate)
+    # batch statistics (include/pdmp_b200.h): batch = global id mod 64, sums shifted by stat_pivot[c]
+    stat_pivot: Optional[np.ndarray] = None   # [C]
+    batch_count: Optional[np.ndarray] = None  # [64, T, C]
+    batch_sum: Optional[np.ndarray] = None    # sum (v - pivot)
+    batch_sumsq: Optional[np.ndarray] = None  # sum (v - pivot)^2
     blocks: Optional[list] = None             # per-device EnsembleResults of a multi-device run
     device: int = 0
     _keep: Any = None
@@ -119,16 +124,42 @@ class EnsembleResult:
                           self.save_positions, int(self.njumps[i]), int(self.nrejected[i]),
                           int(self.status[i]))
 
+    def _shifted(self):
+        """(n, sum (v - p), sum (v - p)^2, p) per (sample time, component): from the batch buffers when present
+        (no cancellation for large means), else from the plain totals with p = 0."""
+        if self.batch_count is not None and self.batch_count.size:
+            return self.batch_count.sum(0), self.batch_sum.sum(0), self.batch_sumsq.sum(0), self.stat_pivot[None, :]
+        return self.stat_count, self.stat_sum, self.stat_sumsq, 0.0
+
     def mean(self):
+        n, a, _, p = self._shifted()
         with np.errstate(invalid="ignore", divide="ignore"):
-            return self.stat_sum / self.stat_count
+            return p + a / n
 
     def var(self):
-        """Unbiased sample variance per (sample time, component)."""
-        n = self.stat_count
+        """Unbiased sample variance per (sample time, component), from the shifted sums."""
+        n, a, q, _ = self._shifted()
         with np.errstate(invalid="ignore", divide="ignore"):
-            m = self.stat_sum / n
-            return (self.stat_sumsq - n * m * m) / (n - 1.0)
+            return (q - a * a / n) / (n - 1.0)
+
+    def batch_means(self):
+        """[64, T, C] mean of every batch (NaN for an empty batch)."""
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return self.stat_pivot[None, None, :] + self.batch_sum / self.batch_count
+
+    def batch_vars(self):
+        n, a, q = self.batch_count, self.batch_sum, self.batch_sumsq
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return (q - a * a / n) / (n - 1.0)
+
+    def mean_stderr(self):
+        """Standard error of mean() by batch means: std of the 64 batch means / 8.  No distributional assumption
+        (the batches are i.i.d. sub-ensembles of equal size up to one trajectory)."""
+        return np.nanstd(self.batch_means(), axis=0, ddof=1) / np.sqrt(np.sum(self.batch_count > 0, axis=0))
+
+    def var_stderr(self):
+        """Standard error of var() by batch variances (replaces a Gaussian-kurtosis guess)."""
+        return np.nanstd(self.batch_vars(), axis=0, ddof=1) / np.sqrt(np.sum(self.batch_count > 1, axis=0))
 
     def status_histogram(self):
         c = np.bincount(self.status, minlength=len(_abi.STATUS_NAMES))

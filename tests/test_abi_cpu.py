@@ -34,7 +34,7 @@ def test_struct_sizes(P):
     assert C.sizeof(P._abi.ModelInfo) == 10 * 4 + 32
     assert C.sizeof(P._abi.ProblemDesc) == 8 * 8 + 4 * 6
     assert C.sizeof(P._abi.SolveOpts) == 8 * 12 + 4 * 16 + 8 * 3 + 4 * 2
-    assert C.sizeof(P._abi.Result) == 8 * 3 + 8 * 11 + 8 * 5 + 8 * 4 + 4 * 8 + 8 + 8 * 3 + 4 * 2
+    assert C.sizeof(P._abi.Result) == 8 * 3 + 8 * 11 + 8 * 5 + 8 * 4 + 4 * 8 + 8 + 8 * 7 + 4 * 2
 
 
 def test_registry_matches_oracle(P, lib, orc):

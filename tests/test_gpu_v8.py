@@ -238,3 +238,84 @@ def test_n_jumps_bound_and_default_attempt_budget(G):
     # the same cap is fine when nothing is saved per jump
     r = G.solve(pb, G.CHVGPU("sir"), trajectories=64, n_jumps=2 ** 40, no_records=True, sample_times=[150.0])
     assert (r.status == G._abi.ST_OK).all() and r.stat_count[0, 0] == 64
+
+
+# ---- ensemble statistics: reproducible, shifted, batched ------------------------
+def test_statistics_are_reproducible_and_batched(G, orc):
+    pb = G.models.problem("tcp2d", tspan=(0.0, 10.0))
+    st = 10.0 * np.arange(1, 9) / 8
+    n = 200_000
+    kw = dict(trajectories=n, n_jumps=2000, seed=5, sample_times=st, hist=[(0, 0.0, 4.0), (2, 0.0, 64.0)], hist_bins=64,
+              no_records=True, traj_id_offset=7)
+    a = G.solve(pb, G.CHVGPU("tcp2d"), **kw)
+    b = G.solve(pb, G.CHVGPU("tcp2d"), **kw)
+    # fixed reduction order: bit-identical from run to run (the round-1 atomics were not)
+    for name in ("stat_count", "stat_sum", "stat_sumsq", "batch_count", "batch_sum", "batch_sumsq", "hist"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    B = G._abi.STAT_BATCHES
+    assert a.batch_count.shape == (B, len(st), 4) and a.stat_pivot.tolist() == [0.05, 0.075, 0.0, 1.0]
+    # batch b holds the trajectories with (global id) mod 64 == b: n / 64 each, up to one
+    per = a.batch_count[:, 0, 0]
+    ids = (np.arange(n) + 7) % B
+    assert np.array_equal(per, np.bincount(ids, minlength=B).astype(float))
+    assert np.array_equal(a.batch_count.sum(0), a.stat_count)
+    # totals are the un-shifted sums of the batches
+    p = a.stat_pivot[None, :]
+    assert np.allclose(a.stat_sum, a.batch_sum.sum(0) + a.stat_count * p, rtol=1e-14, atol=0)
+    # against the oracle on the same stream: same counts, same batch sums to round-off
+    c = orc.solve(pb, "tcp2d", algorithm="chv", ode="dp5", **{**kw, "trajectories": 20_000})
+    g = G.solve(pb, G.CHVGPU("tcp2d"), **{**kw, "trajectories": 20_000})
+    assert np.array_equal(g.batch_count, c.batch_count) and np.array_equal(g.stat_pivot, c.stat_pivot)
+    assert np.allclose(g.batch_sum, c.batch_sum, rtol=1e-6, atol=1e-9) and np.allclose(g.batch_sumsq, c.batch_sumsq, rtol=1e-6, atol=1e-9)
+    assert np.allclose(g.var(), c.var(), rtol=1e-6)
+    # confidence intervals from the batches: the standard error of the mean by batch means agrees with sigma / sqrt(n)
+    se_b, se_v = a.mean_stderr(), np.sqrt(a.var() / a.stat_count)
+    ok = se_v > 0
+    assert np.all(np.abs(se_b[ok] / se_v[ok] - 1.0) < 0.45)          # 64 batches: the ratio has ~9% standard deviation
+    assert np.all(a.var_stderr()[ok] > 0)
+    # an independent ensemble lands inside the batch-means interval (Bonferroni over 8 x 4 comparisons)
+    d = G.solve(pb, G.CHVGPU("tcp2d"), **{**kw, "seed": 6})
+    z = np.abs(a.mean() - d.mean())[ok] / np.sqrt(se_b[ok] ** 2 + d.mean_stderr()[ok] ** 2)
+    assert z.max() < 4.2
+
+
+def test_shifted_sums_keep_the_variance_of_a_large_mean(G):
+    """round 1 formed the variance from sum and sum of squares: for a mean of 1e8 and a spread of 1e-2 that loses
+    every digit.  The pivot (the common initial condition) removes the offset before squaring."""
+    pb = G.models.problem("tcp2d", tspan=(0.0, 2.0))
+    pb.xd0 = np.array([100_000_000, 1])            # xd[0] counts jumps from 1e8: mean ~1e8, spread ~ a few jumps
+    pb.parms = np.array([0.0])                     # the second rate (p xd[0] xc[0]) off: xd[0] only drives the flow's parity
+    r = G.solve(pb, G.CHVGPU("tcp2d"), trajectories=100_000, n_jumps=500, seed=3, sample_times=[1.0, 2.0], no_records=True)
+    q = G.solve(pb, G.CHVGPU("tcp2d"), trajectories=100_000, n_jumps=500, seed=3, sample_times=[1.0, 2.0], no_records=True,
+                xd0=np.tile([100_000_000, 1], (100_000, 1)))      # per-trajectory ICs: pivot 0, the old cancellation
+    v = r.var()[:, 2]
+    assert r.stat_pivot[2] == 1e8 and q.stat_pivot[2] == 0.0
+    assert np.all(v > 0.01) and np.all(v < 100.0)
+    m = r.mean()[:, 2] - 1e8
+    assert np.all(m > 0) and np.all(m < 100)
+    # the naive formula on the un-shifted totals is off by orders of magnitude or negative
+    n = q.stat_count[:, 2]
+    naive = (q.stat_sumsq[:, 2] - q.stat_sum[:, 2] ** 2 / n) / (n - 1)
+    assert np.any(np.abs(naive - v) > 0.5 * v)
+    # and the jump-count spread is the same statistic whatever the offset
+    pb0 = G.models.problem("tcp2d", tspan=(0.0, 2.0)); pb0.parms = np.array([0.0])
+    r0 = G.solve(pb0, G.CHVGPU("tcp2d"), trajectories=100_000, n_jumps=500, seed=3, sample_times=[1.0, 2.0], no_records=True)
+    assert np.allclose(r0.var()[:, 2], v, rtol=1e-9)
+
+
+def test_statistics_chunked_and_multi_device(G, monkeypatch):
+    pb = G.models.problem("tcp", tspan=(0.0, 50.0))
+    n = 40_000
+    xc0 = 0.5 + np.random.default_rng(1).random((n, 1))
+    kw = dict(trajectories=n, n_jumps=300, seed=77, xc0=xc0, sample_times=[10.0, 50.0], hist=[(0, 0.0, 8.0)], hist_bins=32)
+    one = G.solve(pb, G.CHVGPU("tcp"), **kw)
+    monkeypatch.setenv("PDMP_CHUNK", "4096")
+    many = G.solve(pb, G.CHVGPU("tcp"), **kw)                        # 10 chunks on 3 streams, reduced in chunk order
+    again = G.solve(pb, G.CHVGPU("tcp"), **kw)
+    monkeypatch.delenv("PDMP_CHUNK")
+    assert np.array_equal(many.batch_count, one.batch_count) and np.array_equal(many.hist, one.hist)
+    assert np.allclose(many.batch_sum, one.batch_sum, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(many.batch_sum, again.batch_sum) and np.array_equal(many.batch_sumsq, again.batch_sumsq)   # reproducible
+    dev = G.solve(pb, G.CHVGPU("tcp"), devices=[0, 0, 0], **kw)
+    assert np.array_equal(dev.batch_count, one.batch_count) and np.allclose(dev.batch_sum, one.batch_sum, rtol=1e-12, atol=1e-12)
+    assert np.allclose(dev.mean(), one.mean(), rtol=1e-12) and np.allclose(dev.var(), one.var(), rtol=1e-10)
