@@ -42,10 +42,10 @@ TF, N_JUMPS, RELTOL, ABSTOL = 200.0, 1000, 1e-7, 1e-9
 SAMPLE_TIMES = [50.0, 100.0, 150.0, 200.0]
 FLOPS_PER_ATTEMPT_TCP = 180.0   # D*72 + 2 + 10 + 6*C_rhs, D = 2, C_rhs = 4
 REC_BYTES_TCP = 32.0            # 8*(1+n_c) + 8*n_d per saved point; pool record
-CSR_BYTES_TCP = 20.0            # CSR / wire record with int16 xd transport: 8 + 8 + 2*2
+CSR_BYTES_TCP = 17.0            # CSR / wire record with the event transport: 8 (t) + 8 (xc) + 1 (reaction index)
 # DRAM bytes per saved record measured by `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum over the
 # records of that launch; profiles/r1_tcp_kernel_v11_full.txt, profiles/r1_compact_kernel_v11_full.txt)
-NCU_DRAM_BYTES_PER_RECORD = {"ensemble_kernel": 33.1, "compact_kernel": 53.4}
+NCU_DRAM_BYTES_PER_RECORD = {"ensemble_kernel": 33.8, "compact_kernel": 50.4}
 
 
 def workload_config(n_traj, n_gpus):
@@ -56,11 +56,12 @@ def workload_config(n_traj, n_gpus):
         "tstop_policy": "1 on the GPU: after a step clipped by a jump threshold the proposal never drops below the "
                         "pending unclipped one (every step stays error-controlled); the CPU arm keeps OrdinaryDiffEq's rule",
         "save_positions": [False, True], "sample_times": SAMPLE_TIMES,
-        "xd_transport": "auto -> int16 (|xd| <= 1 + 999 is provable for TCP with n_jumps = 1000; widened to the reference's "
-                        "Int64 per trajectory on access): a saved point is 8 (t) + 8 (xc) + 2 x 2 (xd) = 20 B on the wire",
+        "xd_transport": "auto -> event (no Delta and |xd| <= 1 + 999 < 2^23 are provable for TCP with n_jumps = 1000): the wire "
+                        "carries the index of the reaction behind every saved point and the binding rebuilds the reference's Int64 "
+                        "xd as xd0 + a prefix sum of nu rows on access; a saved point is 8 (t) + 8 (xc) + 1 = 17 B on the wire",
         "initial_conditions": "synthetic xc0_i = 0.5 + u_i (numpy PCG64 seed 2024), xd0 = [0, 1]",
         "rng": "philox4x32-10, seed = step index",
-        "l2": "working set (42 GB of pool records + 26 GB of CSR per step) is far larger than the 126 MB L2; no flush needed",
+        "l2": "working set (42 GB of pool records + 22 GB of CSR per step) is far larger than the 126 MB L2; no flush needed",
         "parallelism": f"ensemble sharding x{n_gpus} (contiguous global id ranges), stats all-reduce only",
     }
 
@@ -141,6 +142,31 @@ def host_ics(n, pinned=True):
     return t, a
 
 
+def pcie_peak(torch, dist, world, nbytes=1 << 30):
+    """Pinned-memory copy peaks of this box, all ranks at once (plain cudaMemcpyAsync through torch): the denominator
+    of the end-to-end roofline.  Returns (d2h GB/s aggregate, h2d GB/s aggregate)."""
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    out = []
+    for dst, src in ((h, d), (d, h)):
+        best = 0.0
+        for rep_ in range(3):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); dst.copy_(src, non_blocking=True); b.record()
+            torch.cuda.synchronize()
+            if rep_:
+                best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+        t = torch.tensor([best], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t)
+        out.append(float(t.item()))
+    del h, d
+    return out
+
+
 def cpu_baseline(n_sample, threads=None, ode="tsit5"):
     """The oracle port on the host cores: a bounded sample of the same workload."""
     import oracle as orc
@@ -210,10 +236,29 @@ def run_gpu(args):
     n = args.traj
     pb = P.models.problem("tcp", tspan=(0.0, TF))
     ics_t, ics = host_ics(n)
-    mk = lambda ntr, ic: P.Ensemble(pb, P.CHVGPU("tcp", ode="dp5"), trajectories=ntr, traj_id_offset=rank * n,
-                                    n_jumps=N_JUMPS, reltol=RELTOL, abstol=ABSTOL, save_positions=(False, True),
-                                    sample_times=SAMPLE_TIMES, device=local, max_records=int(ntr * 160), xc0=ic,
-                                    tstop_policy=1, xd_transport="auto")
+    def mk(ntr, ic, policy=1):
+        return P.Ensemble(pb, P.CHVGPU("tcp", ode="dp5"), trajectories=ntr, traj_id_offset=rank * n,
+                          n_jumps=N_JUMPS, reltol=RELTOL, abstol=ABSTOL, save_positions=(False, True),
+                          sample_times=SAMPLE_TIMES, device=local, max_records=int(ntr * 160), xc0=ic,
+                          tstop_policy=policy, xd_transport="auto")
+    # the same resident step under OrdinaryDiffEq's own step rule (tstop_policy 0), reported next to the headline
+    value_pol0 = None
+    if not args.no_policy0:
+        e0 = mk(n, ics, policy=0)
+        for s in range(2):
+            e0.run(seed=2000 + s)
+            e0.counters()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        j0 = at0 = 0
+        for s in range(2):
+            e0.run(seed=s, stream=torch.cuda.current_stream().cuda_stream)
+            c0 = e0.counters(); j0 += c0["total_jumps"]; at0 += c0["rk_attempts"]
+        b.record(); torch.cuda.synchronize()
+        value_pol0 = {"value": j0 / (a.elapsed_time(b) * 1e-3), "unit": UNIT, "rk_attempts_per_jump": at0 / max(j0, 1), "steps": 2,
+                      "note": "rank 0's GPU only; tstop_policy 0 = OrdinaryDiffEq's h_clipped/q after a step clipped by a threshold"}
+        e0.close(); del e0
     ens = mk(n, ics)
     n_chunks = 1 if n <= 2 * (1 << 20) else -(-n // (1 << 20))
     stats_t, hist_t = P.distributed.stats_tensors(ens, dev)   # zero-copy torch views of the library's buffers
@@ -230,6 +275,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     fp64_peak = P.fp64_peak_tflops(local)
+    d2h_peak, h2d_peak = pcie_peak(torch, dist, world)
     for s in range(args.warmup):
         step(1000 + s)
     barrier()
@@ -287,8 +333,9 @@ def run_gpu(args):
         if world > 1:
             P.distributed.allreduce_stats_host(r)   # global statistics on every rank
         ej += r.counters["total_jumps"]
-        d2h_bytes = (r.time.nbytes + r.xc.nbytes + r.xd.nbytes + r.offsets.nbytes + r.njumps.nbytes +
-                     r.nrejected.nbytes + r.status.nbytes + r.stat_count.nbytes * 3)
+        xd_wire = r._xd_raw if r._event is not None else r.xd     # (touching r.xd would rebuild it from the event bytes)
+        d2h_bytes = (r.time.nbytes + r.xc.nbytes + xd_wire.nbytes + r.offsets.nbytes + r.njumps.nbytes +
+                     r.nrejected.nbytes + r.status.nbytes + r.batch_count.nbytes * 3)
         del r
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -319,10 +366,16 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ics_e.nbytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps, "trajectories_per_gpu": n_e2e,
                     "ms_per_step": 1e3 * float(e.item()) / e2e_steps},
-            "gpu_launches": 3 * args.steps,
-            "gpu_launches_note": "timed (resident) region, per step: ensemble_kernel + chunk_close_kernel + compact_kernel, ours; "
-                                 "plus cub::DeviceScan and memsets.  The e2e region launches the same three per chunk "
-                                 f"({n_chunks} chunks per step)",
+            "roofline_e2e": {"bound": "pcie", "achieved": world * d2h_bytes / (float(e.item()) / e2e_steps) / 1e9, "peak": d2h_peak,
+                             "unit": "GB/s", "frac": world * d2h_bytes / (float(e.item()) / e2e_steps) / 1e9 / d2h_peak,
+                             "h2d_peak": h2d_peak,
+                             "note": "device->host bytes of one e2e step (all ranks) / its wall time, against the pinned D2H copy "
+                                     "peak of this box measured in this run with all ranks copying at once"},
+            "value_tstop_policy0": value_pol0,
+            "gpu_launches": 4 * args.steps,
+            "gpu_launches_note": "timed (resident) region, per step: ensemble_kernel + stats_reduce_kernel + chunk_close_kernel + "
+                                 "compact_kernel, ours; plus cub::DeviceScan and memsets.  The e2e region launches the same four per "
+                                 f"chunk ({n_chunks} chunks per step)",
             "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
                          "traffic": NCU_DRAM_BYTES_PER_RECORD["ensemble_kernel"] * records / args.steps,
                          "traffic_note": "bytes per launch = ncu-measured DRAM bytes per saved record (profiles/) x records of one "
@@ -351,6 +404,56 @@ def run_gpu(args):
     return 0
 
 
+def run_single_process(args):
+    """--single-process: ONE process drives all N GPUs through the library's own sharding (pdmp_solve_opts.devices):
+    one host thread per device inside libpdmp_b200.so, statistics summed there.  The same workload and step as the
+    torchrun path, for comparison with it (SURVEY.md 8(b) "device list")."""
+    import torch
+    import pdmp_b200 as P
+    G = args.gpus
+    if P.device_count() < G:
+        raise RuntimeError(f"--single-process --gpus {G}: only {P.device_count()} CUDA devices")
+    n = args.traj * G
+    pb = P.models.problem("tcp", tspan=(0.0, TF))
+    ics_t, ics = host_ics(n)
+    ens = P.Ensemble(pb, P.CHVGPU("tcp", ode="dp5"), trajectories=n, n_jumps=N_JUMPS, reltol=RELTOL, abstol=ABSTOL,
+                     save_positions=(False, True), sample_times=SAMPLE_TIMES, devices=list(range(G)),
+                     max_records=int(n * 160), xc0=ics, tstop_policy=1, xd_transport="auto")
+    sync = lambda: [torch.cuda.synchronize(g) for g in range(G)]
+    for s in range(args.warmup):
+        ens.run(seed=1000 + s); ens.counters()
+    sync()
+    clocks = ClockSampler(0); clocks.start()
+    t0 = time.perf_counter()
+    jumps = attempts = 0
+    kernel_ms = 0.0
+    for s in range(args.steps):
+        ens.run(seed=s)
+        c = ens.counters()        # waits for every shard: device work of the step is complete
+        jumps += c["total_jumps"]; attempts += c["rk_attempts"]; kernel_ms += c["kernel_ms"]
+    sync()
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    r = ens.run_host(seed=999, xc0=ics); del r
+    t1 = time.perf_counter(); ej = 0
+    for s in range(e2e_steps):
+        r = ens.run_host(seed=s, xc0=ics); ej += r.counters["total_jumps"]; del r
+    e2e_s = time.perf_counter() - t1
+    line = {"metric": METRIC, "value": jumps / dt, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(workload_config(args.traj, G), mode="single process, opts.devices (one host thread "
+                                                                                   "per GPU inside the library)"),
+            "trajectories_per_sec": n * args.steps / dt, "rk_attempts_per_jump": attempts / max(jumps, 1),
+            "kernel_ms_per_step_max_over_devices": kernel_ms / args.steps,
+            "e2e": {"value": ej / e2e_s, "unit": UNIT, "steps": e2e_steps, "h2d_bytes_per_step": int(ics.nbytes)},
+            "gpu_launches": 4 * args.steps * G, "clocks": clk,
+            "timing": "host wall clock around K steps, every device synchronised on both sides"}
+    print(json.dumps(line))
+    ens.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -361,9 +464,14 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=1_500_000, help="trajectories of the CPU baseline sample (~15 s on 16 cores)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-policy0", action="store_true", help="skip the extra resident measurement under tstop_policy 0")
+    ap.add_argument("--single-process", action="store_true",
+                    help="N > 1 without torchrun: ONE process, the ensemble sharded over N GPUs inside the library call (opts.devices)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.single_process and args.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        return run_single_process(args)
     return run_gpu(args)
 
 

@@ -177,6 +177,12 @@ typedef struct pdmp_solve_opts {
                                      2: int16 — the caller asserts |xd| < 32768 for the whole
                                         run (e.g. |xd0| + n_jumps max|nu| without a Delta);
                                         the host bindings check this bound before asking.
+                                     1: event transport — ONE byte per saved point: the index (1-based) of
+                                        the reaction that changed xd since the trajectory's previous saved
+                                        point, 0 for none (initial / final / pre-jump points).  xd is rebuilt
+                                        by the bindings as xd0 + a prefix sum of nu rows.  Only for models
+                                        without a Delta and |xd0| + (n_jumps - 1) max|nu| < 2^23 (checked by
+                                        the library: PDMP_ERR_UNSUPPORTED otherwise).
                                      Narrow transport cuts the device->host bytes per saved
                                      point; the bindings widen per trajectory on access.    */
     int32_t save_c_count;         /* REJECTION_EXACT: save only the first save_c_count
@@ -212,7 +218,8 @@ typedef struct pdmp_result {
     double* time;              /* [total_records]                                          */
     double* xc;                /* [total_records][n_c]                                     */
     void* xd;                  /* [total_records][n_d], elements of xd_bytes bytes (int64
-                                  unless opts.xd_bytes asked for a narrower transport)    */
+                                  unless opts.xd_bytes asked for a narrower transport);
+                                  xd_bytes = 1: [total_records] reaction indices (uint8)   */
     int64_t* njumps;           /* [n_traj] PDMPResult.njumps (src/utils.jl:79)             */
     int64_t* nrejected;        /* [n_traj] PDMPResult.nrejected (fictitous_jumps)          */
     uint8_t* status;           /* [n_traj] PDMP_ST_*                                       */

@@ -28,9 +28,10 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
     xc0 / xd0 override the problem's (broadcast) initial conditions with per-trajectory
     arrays [trajectories, n_c] / [trajectories, n_d].
     hist: list of (component, lo, hi).
-    xd_transport: "int64" (reference layout), "int32" (always exact), "int16", or "auto" = the
-    narrowest width that provably holds |xd0| + (n_jumps - 1) max|nu| (int32 when the model has a
-    Delta, which may move xd arbitrarily).
+    xd_transport: "int64" (reference layout), "int32" (always exact), "int16", "event" (ONE byte per saved
+    point: the index of the reaction that produced it; xd is rebuilt on access as xd0 + a prefix sum of nu
+    rows — for models without a Delta and |xd| provably below 2^23), or "auto" = the narrowest of these
+    that is provably exact (int32 when the model has a Delta, which may move xd arbitrarily).
     devices: list of CUDA ordinals; the ensemble is sharded over them inside the library call.
     save_rate: also return the total rate at every saved jump (reference `save_rate` / PDMPResult.rates).
     ind_save_c / ind_save_d: 0-based indices of the continuous / discrete components to save (the
@@ -115,10 +116,15 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
     o.ref_quirks = int(bool(ref_quirks))
     bound = int(np.max(np.abs(xd), initial=0)) + max(int(n_jumps) - 1, 0) * int(np.max(np.abs(nu), initial=0))
     if xd_transport == "auto":
-        xd_transport = "int16" if (bound < 32768 and not info.has_delta) else "int32"
+        xd_transport = "int32" if info.has_delta else ("event" if (bound < 2 ** 23 and ind_save_d is None) else
+                                                        "int16" if bound < 32768 else "int32")
+    if xd_transport == "event" and (bound >= 2 ** 23 or info.has_delta or ind_save_d is not None):
+        raise ValueError("xd_transport='event' needs a model without a Delta, all of xd saved and |xd| < 2^23 (bound %d)" % bound)
     if xd_transport == "int16" and (bound >= 32768 or info.has_delta):
         raise ValueError("xd_transport='int16' is not provably exact for this problem (bound %d)" % bound)
-    o.xd_bytes = {"int64": 8, "int32": 4, "int16": 2}[xd_transport]
+    o.xd_bytes = {"int64": 8, "int32": 4, "int16": 2, "event": 1}[xd_transport]
+    if xd_transport == "event":     # what the bindings need to rebuild xd from the reaction indices
+        keep.append(dict(event_nu=nu.copy(), event_xd0=xd.copy()))
     o.save_c_count, o.save_d_count = int(save_c_count), int(save_d_count)
     if devices is not None:
         dv = np.ascontiguousarray(devices, dtype=np.int32).reshape(-1)
@@ -153,9 +159,11 @@ def _arr(ptr, shape, dtype, copy):
 
 
 def to_numpy(res, *, copy=True, save_positions=(False, True), sample_times=None, keep=None,
-             records=True):
+             records=True, event=None):
+    """event: dict(event_nu, event_xd0) when the run used xd_transport='event' (see build())."""
     if int(res.n_blocks) > 1:
-        return _from_blocks(res, copy=copy, save_positions=save_positions, sample_times=sample_times, keep=keep, records=records)
+        return _from_blocks(res, copy=copy, save_positions=save_positions, sample_times=sample_times, keep=keep, records=records,
+                            event=event)
     n, tot = int(res.n_traj), int(res.total_records) if records else 0
     T, Cc, H, B = res.n_sample_times, res.n_comp, res.hist_n, res.hist_bins
     nc, nd = res.n_c, res.n_d
@@ -164,7 +172,8 @@ def to_numpy(res, *, copy=True, save_positions=(False, True), sample_times=None,
         offsets=_arr(res.offsets, (n + 1,), np.uint64, copy) if records else np.zeros(n + 1, np.uint64),
         time=_arr(res.time, (tot,), np.float64, copy),
         xc=_arr(res.xc, (tot, nc), np.float64, copy),
-        xd=_arr(res.xd, (tot, nd), {8: np.int64, 4: np.int32, 2: np.int16}[int(res.xd_bytes) or 8], copy),
+        xd=(_arr(res.xd, (tot,), np.uint8, copy) if int(res.xd_bytes) == 1 else
+            _arr(res.xd, (tot, nd), {8: np.int64, 4: np.int32, 2: np.int16}[int(res.xd_bytes) or 8], copy)),
         njumps=_arr(res.njumps, (n,), np.int64, copy),
         nrejected=_arr(res.nrejected, (n,), np.int64, copy),
         status=_arr(res.status, (n,), np.uint8, copy),
@@ -187,22 +196,26 @@ def to_numpy(res, *, copy=True, save_positions=(False, True), sample_times=None,
         sample_times=None if sample_times is None else np.array(sample_times, dtype=np.float64),
         _keep=keep,
     )
+    if int(res.xd_bytes) == 1:
+        if event is None:
+            raise ValueError("event transport: the decoding tables (nu, xd0) are missing")
+        out._set_event_transport(event["event_nu"], event["event_xd0"], int(res.traj_begin))
     return out
 
 
-def _from_blocks(res, *, copy, save_positions, sample_times, keep, records):
+def _from_blocks(res, *, copy, save_positions, sample_times, keep, records, event=None):
     """Multi-device result: one block per device shard (include/pdmp_b200.h, pdmp_result.blocks).  The blocks
     stay separate views (`out.blocks`); the flat arrays of the EnsembleResult are their concatenation
     (a host copy), with the offsets rebased, so that `res[i]` and the whole-array properties work unchanged."""
     blocks = [to_numpy(res.blocks[g], copy=copy, save_positions=save_positions, sample_times=sample_times, keep=keep,
-                       records=records) for g in range(int(res.n_blocks))]
+                       records=records, event=event) for g in range(int(res.n_blocks))]
     for g, b in enumerate(blocks):
         b.shard = (int(res.blocks[g].traj_begin), b.n_traj)
         b.device = int(res.blocks[g].device)
     T, Cc, H, B = res.n_sample_times, res.n_comp, res.hist_n, res.hist_bins
     base = np.cumsum([0] + [len(b.time) for b in blocks])
     offsets = np.concatenate([b.offsets[:-1] + np.uint64(base[g]) for g, b in enumerate(blocks)] + [np.array([base[-1]], np.uint64)])
-    cat = lambda name: np.concatenate([getattr(b, name) for b in blocks])
+    cat = lambda name: np.concatenate([getattr(b, "_xd_raw" if name == "xd" and b._event is not None else name) for b in blocks])
     out = EnsembleResult(
         n_traj=int(res.n_traj), n_c=res.n_c, n_d=res.n_d, offsets=offsets, time=cat("time"), xc=cat("xc"), xd=cat("xd"),
         njumps=cat("njumps"), nrejected=cat("nrejected"), status=cat("status"),
@@ -220,4 +233,6 @@ def _from_blocks(res, *, copy, save_positions, sample_times, keep, records):
         save_positions=tuple(bool(x) for x in save_positions),
         sample_times=None if sample_times is None else np.array(sample_times, dtype=np.float64), _keep=keep)
     out.blocks = blocks
+    if blocks[0]._event is not None:
+        out._set_event_transport(event["event_nu"], event["event_xd0"], 0)
     return out

@@ -167,6 +167,7 @@ struct pdmp_ensemble {
     unsigned long long* d_offsets = nullptr; double* d_time = nullptr; double* d_xc = nullptr; unsigned char* d_xd = nullptr;
     double* d_rate_pool[NS] = {}; double* d_rate = nullptr;   // save_rate: total rate per pool slot / per CSR record
     int nco = 0, ndo = 0;   // saved components per point (ind_save_c / ind_save_d)
+    size_t xrec = 0;        // bytes of discrete state per saved point in the CSR: ndo * xb, or 1 under the event transport
     int xb = 8;  // bytes per saved discrete component (opts.xd_bytes)
     void* d_scan[NS] = {}; size_t scan_bytes = 0;
     unsigned long long csr_cap = 0, pool_blocks = 0;
@@ -399,7 +400,10 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     if (o->ode != PDMP_ODE_DP5 && o->ode != PDMP_ODE_TSIT5) return fail(PDMP_ERR_INVALID, "ode");
     if (o->precision != PDMP_PREC_FP64 && o->precision != PDMP_PREC_FP32) return fail(PDMP_ERR_INVALID, "precision");
     if (o->rng_mode == PDMP_RNG_REPLAY && (!o->replay_u || !o->replay_stride)) return fail(PDMP_ERR_INVALID, "replay_u");
-    if (o->xd_bytes != 0 && o->xd_bytes != 8 && o->xd_bytes != 4 && o->xd_bytes != 2) return fail(PDMP_ERR_INVALID, "xd_bytes must be 0, 8, 4 or 2");
+    if (o->xd_bytes != 0 && o->xd_bytes != 8 && o->xd_bytes != 4 && o->xd_bytes != 2 && o->xd_bytes != 1)
+        return fail(PDMP_ERR_INVALID, "xd_bytes must be 0, 8, 4, 2 or 1");
+    if (o->xd_bytes == 1 && (m.info.has_delta || o->save_d_mask))
+        return fail(PDMP_ERR_UNSUPPORTED, "xd_bytes = 1 (event transport) needs xd to change through nu alone (no Delta) and all of xd saved");
     if (o->hist_n < 0 || o->hist_n > MAXH) return fail(PDMP_ERR_INVALID, "hist_n must be <= 4");
     if (o->hist_n && o->hist_bins < 1) return fail(PDMP_ERR_INVALID, "hist_bins");
     if (d->n_traj > 0xfffffff0ull) return fail(PDMP_ERR_INVALID, "n_traj per call must be < 2^32");
@@ -417,6 +421,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         e->P.save_d_mask = o->save_d_mask ? o->save_d_mask : alld;
         e->nco = __builtin_popcountll(e->P.save_c_mask); e->ndo = __builtin_popcountll(e->P.save_d_mask);
         e->P.n_c_out = e->nco; e->P.n_d_out = e->ndo;
+        e->xrec = e->xb == 1 ? 1 : (size_t)e->ndo * e->xb;
     }
     for (auto& st : e->cs) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
@@ -453,10 +458,21 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         }
     {
         const size_t nchk = (size_t)(d->xd0_per_traj ? d->n_traj : 1) * ND;
-        for (size_t i = 0; i < nchk; ++i)
+        long long amax = 0;
+        for (size_t i = 0; i < nchk; ++i) {
             if (d->xd0[i] > 0x3fffffffLL || d->xd0[i] < -0x3fffffffLL)
                 return fail(PDMP_ERR_INVALID, "xd0 entries must fit in 31 bits");
+            amax = std::max<long long>(amax, std::llabs(d->xd0[i]));
+        }
+        if (o->xd_bytes == 1) {   // the event index shares xd[0]'s pool word: |xd| < 2^23 must hold for the whole run
+            long long numax = 0;
+            for (int i = 0; i < NR * ND; ++i) numax = std::max<long long>(numax, std::abs((long long)P.nu[i]));
+            const long double bound = (long double)amax + (long double)std::max<long long>(o->n_jumps - 1, 0) * (long double)numax;
+            if (bound >= (long double)(1 << 23))
+                return fail(PDMP_ERR_UNSUPPORTED, "xd_bytes = 1: |xd0| + (n_jumps - 1) max|nu| must stay below 2^23");
+        }
     }
+    P.ev_pack = o->xd_bytes == 1;
     P.t0 = d->t0; P.tf = d->tf;
     P.rate_const = d->rate_kind == 1;
     P.rate_composite = d->rate_kind == 2;
@@ -555,7 +571,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         const unsigned long long maxrec = max_records_per_traj(*o);
         P.table_w = table_width(maxrec);
         const size_t rec_bytes = (size_t)m.rec_words * 8 + (o->save_rate ? 8 : 0);
-        const size_t csr_bytes = (size_t)8 * (1 + e->nco) + (size_t)e->xb * e->ndo + (o->save_rate ? 8 : 0);
+        const size_t csr_bytes = (size_t)8 * (1 + e->nco) + e->xrec + (o->save_rate ? 8 : 0);
         const unsigned long long per_traj_worst = pool_records_for(maxrec);
         const unsigned long long worst = n * per_traj_worst;
         int npools = std::min(NS, e->n_chunks);
@@ -605,7 +621,7 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         CK(cudaMemsetAsync(e->d_offsets, 0, sizeof(unsigned long long), s0));
         CK(cudaMalloc(&e->d_time, std::max<size_t>(e->csr_cap, 1) * sizeof(double)));
         CK(cudaMalloc(&e->d_xc, std::max<size_t>(e->csr_cap * e->nco, 1) * sizeof(double)));
-        CK(cudaMalloc(&e->d_xd, std::max<size_t>(e->csr_cap * e->ndo, 1) * e->xb));
+        CK(cudaMalloc(&e->d_xd, std::max<size_t>(e->csr_cap * e->xrec, 1)));
         P.seg_table = e->d_segtab; P.pool_blocks = e->pool_blocks;
         CK(cub::DeviceScan::ExclusiveScan(nullptr, e->scan_bytes, e->d_nrec, e->d_offsets, AddULL(),
                                           cub::FutureValue<unsigned long long>(e->d_offsets), (long long)n, s0));
@@ -690,7 +706,7 @@ static int queue_chunk_d2h(pdmp_ensemble* e, int k, bool fetch_records) {
         if (r1 > r0) {
             CK(cudaMemcpyAsync(e->h_time.p + r0, e->d_time + r0, (r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(e->h_xc.p + r0 * NC, e->d_xc + r0 * NC, (r1 - r0) * NC * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(e->h_xd.p + r0 * ND * e->xb, e->d_xd + r0 * ND * e->xb, (r1 - r0) * ND * e->xb, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(e->h_xd.p + r0 * e->xrec, e->d_xd + r0 * e->xrec, (r1 - r0) * e->xrec, cudaMemcpyDeviceToHost, st));
             if (e->d_rate) CK(cudaMemcpyAsync(e->h_rate.p + r0, e->d_rate + r0, (r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, st));
         }
     }
@@ -709,7 +725,7 @@ static int run_pipeline(pdmp_ensemble* e, uint64_t seed, cudaStream_t user, bool
         CK(e->h_njumps.reserve(e->n)); CK(e->h_nrej.reserve(e->n)); CK(e->h_status.reserve(e->n));
         if (fetch_records && e->records) {
             CK(e->h_offsets.reserve(e->n + 1)); CK(e->h_time.reserve_exact(e->csr_cap));
-            CK(e->h_xc.reserve_exact(e->csr_cap * e->nco)); CK(e->h_xd.reserve_exact(e->csr_cap * e->ndo * e->xb));
+            CK(e->h_xc.reserve_exact(e->csr_cap * e->nco)); CK(e->h_xd.reserve_exact(e->csr_cap * e->xrec));
             if (e->d_rate) CK(e->h_rate.reserve_exact(e->csr_cap));
         }
     }
@@ -927,12 +943,12 @@ int32_t pdmp_ensemble_fetch(pdmp_ensemble* e, int32_t fetch_records, pdmp_result
     const size_t total = recs ? (size_t)r->total_records : 0;
     if (recs) {
         CK(e->h_offsets.reserve(n + 1)); CK(e->h_time.reserve(total)); CK(e->h_xc.reserve(total * NC));
-        CK(e->h_xd.reserve(total * ND * e->xb));
+        CK(e->h_xd.reserve(total * e->xrec));
         CK(cudaMemcpyAsync(e->h_offsets.p, e->d_offsets, (n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         if (total) {
             CK(cudaMemcpyAsync(e->h_time.p, e->d_time, total * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(e->h_xc.p, e->d_xc, total * NC * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(e->h_xd.p, e->d_xd, total * ND * e->xb, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(e->h_xd.p, e->d_xd, total * e->xrec, cudaMemcpyDeviceToHost, st));
             if (e->d_rate) { CK(e->h_rate.reserve(total)); CK(cudaMemcpyAsync(e->h_rate.p, e->d_rate, total * sizeof(double), cudaMemcpyDeviceToHost, st)); }
         }
     }

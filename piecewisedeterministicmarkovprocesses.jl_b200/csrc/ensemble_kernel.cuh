@@ -66,6 +66,8 @@ struct KParams {
     double* rate_pool;              // save_rate: total rate per pool record slot (null: not saved)
     unsigned long long save_c_mask, save_d_mask;   // ind_save_c / ind_save_d as bit masks (compaction only)
     int n_c_out, n_d_out;           // saved component counts = popcount of the masks
+    int ev_pack;                    // event transport (xd_bytes = 1): the reaction index rides in the top byte of xd[0]'s
+                                    // pool word (the library has checked |xd| < 2^23 for the whole run)
     // per-trajectory outputs
     unsigned long long* nrec;       // [n_traj + 1], records stored per trajectory
     long long* njumps;
@@ -180,8 +182,9 @@ struct Traj {
 
     // ---- record pool writer ----------------------------------------------------------
     PDMP_DEV static double no_rate() { return __longlong_as_double(0x7ff8000000000000ll); }   // NaN: no jump produced this point
-    PDMP_DEV void write_record(const KParams& P, double t, const R* xc) { write_record(P, t, xc, no_rate()); }
-    PDMP_DEV void write_record(const KParams& P, double t, const R* xc, double rate_tot) {
+    PDMP_DEV void write_record(const KParams& P, double t, const R* xc) { write_record(P, t, xc, no_rate(), 0); }
+    // ev: the reaction (1-based) that changed xd since this trajectory's previous saved point, 0 if none
+    PDMP_DEV void write_record(const KParams& P, double t, const R* xc, double rate_tot, int ev) {
         if constexpr (!RECORDS) return;
         if (seg_left == 0) {
             const unsigned nrecs = seg_records(seg_k);
@@ -203,7 +206,8 @@ struct Traj {
         for (int i = 0; i < NC; ++i) w[1 + i] = (double)xc[i];
 #pragma unroll
         for (int i = 0; i < RL::XD_WORDS; ++i) {
-            const int lo = xd[2 * i];
+            int lo = xd[2 * i];
+            if (i == 0 && P.ev_pack) lo = (lo & 0x00ffffff) | (ev << 24);
             const int hi = (2 * i + 1 < ND) ? xd[2 * i + 1] : 0;
             w[1 + NC + i] = __hiloint2double(hi, lo);
         }
@@ -443,8 +447,9 @@ struct Traj {
         R tot = rate[0];
 #pragma unroll
         for (int i = 1; i < NR; ++i) tot += rate[i];  // sum(rate), left to right
-        if (P.save_pre && tj <= P.tf) write_record(P, tj, y, (double)tot);  // :41-48
+        if (P.save_pre && tj <= P.tf) write_record(P, tj, y, (double)tot, 0);  // :41-48
         double u_exp;
+        int ev_done = 0;
         if (tj < P.tf) {  // :52
             // a positive finite total is required where pfsample uses it; at the overshoot threshold the
             // reference computes the rates and ignores them
@@ -467,6 +472,7 @@ struct Traj {
 #pragma unroll
             for (int i = 0; i < ND; ++i) xd[i] += P.nu[(ev - 1) * ND + i];
             if constexpr (M::HAS_DELTA) M::delta(y, xd, P.parms, tj, ev);
+            ev_done = ev;
             refresh_rate(P, tj);
             field(P, y, k1, (R)tstop);  // u_modified!(integrator, true): FSAL re-evaluated (s = tstop here)
 #pragma unroll
@@ -484,7 +490,7 @@ struct Traj {
         }
         if (!(tlast < tj)) { finish(P, PDMP_ST_NO_PROGRESS); return true; }  // @assert :145
         tlast = tj;                       // :146
-        if (P.save_post && tj <= P.tf) write_record(P, tj, xs, tj < P.tf ? (double)tot : no_rate());  // :149-156
+        if (P.save_post && tj <= P.tf) write_record(P, tj, xs, tj < P.tf ? (double)tot : no_rate(), ev_done);  // :149-156
         return epilogue(P, ex, aux, fail);
     }
 
@@ -506,6 +512,7 @@ struct Traj {
         const bool reject = u_acc < 1.0 - (double)tot / (double)bnd;         // :35
         const double dtn = neg_log_unit(u_exp) / (double)bnd;                        // :36
         const bool fire = tc < P.tf && !reject;
+        int ev_done = 0;
         if (fire) {                                          // :41
             const R thr = (R)draw(P, ex) * tot;              // :55
             int ev = 1;
@@ -516,6 +523,7 @@ struct Traj {
 #pragma unroll
             for (int i = 0; i < ND; ++i) xd[i] += P.nu[(ev - 1) * ND + i];
             if constexpr (M::HAS_DELTA) M::delta(y, xd, P.parms, tc, ev);
+            ev_done = ev;
             field(P, y, k1, (R)tc);
             ++simnj;                                         // :64
             ++jumps;
@@ -535,7 +543,7 @@ struct Traj {
         r = tstop - tc;
         if (tlast >= tc) { finish(P, PDMP_ST_NO_PROGRESS); return true; }  // :121-124
         tlast = tc;
-        if (P.save_post && tc <= P.tf && !reject) write_record(P, tc, y, (double)tot);  // :128-138
+        if (P.save_post && tc <= P.tf && !reject) write_record(P, tc, y, (double)tot, ev_done);  // :128-138
         return epilogue(P, ex, aux, fail);
     }
 };
@@ -765,7 +773,10 @@ PDMP_DEV void csr_store(const double (&w)[RecLayout<M>::WORDS], unsigned long lo
     __stcs(time + o, w[0]);
 #pragma unroll
     for (int c = 0; c < NC; ++c) __stcs(xc + o * NC + c, w[1 + c]);
-    if constexpr (sizeof(XT) == 2 && ND % 2 == 0) {
+    if constexpr (sizeof(XT) == 1) {
+        // event transport: ONE byte per saved point, the reaction index (the bindings rebuild xd by a prefix sum over nu)
+        __stcs(reinterpret_cast<unsigned char*>(xd) + o, (unsigned char)((unsigned)__double2loint(w[1 + NC]) >> 24));
+    } else if constexpr (sizeof(XT) == 2 && ND % 2 == 0) {
         // int16 transport: a pair of components is one 32-bit store
         unsigned* dst = reinterpret_cast<unsigned*>(xd + o * ND);
 #pragma unroll
@@ -800,6 +811,10 @@ PDMP_DEV void csr_store_masked(const double (&w)[RecLayout<M>::WORDS], unsigned 
 #pragma unroll
     for (int c = 0; c < NC; ++c)
         if ((cmask >> c) & 1ull) { xc[o * nco + k] = w[1 + c]; ++k; }
+    if constexpr (sizeof(XT) == 1) {   // event transport: the reaction index, whatever the masks
+        __stcs(reinterpret_cast<unsigned char*>(xd) + o, (unsigned char)((unsigned)__double2loint(w[1 + NC]) >> 24));
+        return;
+    }
     k = 0;
 #pragma unroll
     for (int c = 0; c < ND; ++c)
@@ -930,6 +945,7 @@ cudaError_t model_compact(const KParams& P, const unsigned long long* offsets, d
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (xd_bytes == 1) return compact_launch<M, unsigned char>(co_resident, P, offsets, time, xc, (unsigned char*)xd, rate, sms, st);
     if (xd_bytes == 2) return compact_launch<M, short>(co_resident, P, offsets, time, xc, (short*)xd, rate, sms, st);
     if (xd_bytes == 4) return compact_launch<M, int>(co_resident, P, offsets, time, xc, (int*)xd, rate, sms, st);
     return compact_launch<M, long long>(co_resident, P, offsets, time, xc, (long long*)xd, rate, sms, st);

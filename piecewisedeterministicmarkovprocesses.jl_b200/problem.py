@@ -107,12 +107,45 @@ class EnsembleResult:
     blocks: Optional[list] = None             # per-device EnsembleResults of a multi-device run
     device: int = 0
     _keep: Any = None
+    _event: Any = None            # (nu_ext [n_r + 1, n_d], xd0, first global index) under the event transport
+    _xd_raw: Any = None           # the reaction indices as shipped (uint8 [total])
+    _xd_full: Any = None
+
+    def _set_event_transport(self, nu, xd0, traj_begin):
+        """xd arrived as ONE byte per saved point (the reaction index, 0 = none): keep the bytes, rebuild xd lazily."""
+        nu_ext = np.vstack([np.zeros((1, nu.shape[1]), np.int64), nu.astype(np.int64)])
+        object.__setattr__(self, "_event", (nu_ext, np.asarray(xd0, np.int64), int(traj_begin)))
+        object.__setattr__(self, "_xd_raw", self.__dict__["xd"])
+        self.__dict__.pop("xd", None)
+
+    def _event_xd0(self, i):
+        nu_ext, xd0, begin = self._event
+        return xd0[begin + i] if xd0.ndim == 2 else xd0
+
+    def __getattr__(self, name):
+        # only reached for attributes that are not set: `xd` under the event transport
+        if name == "xd" and self.__dict__.get("_event") is not None:
+            if self._xd_full is None:
+                nu_ext, xd0, begin = self._event
+                cs = np.cumsum(nu_ext[self._xd_raw], axis=0)                 # prefix sum of nu rows over the whole CSR
+                first = self.offsets[:-1].astype(np.int64)
+                cnt = np.diff(self.offsets.astype(np.int64))
+                base = cs[first] if len(cs) else cs[:0]                     # a trajectory's first point carries event 0
+                x0 = xd0[begin:begin + self.n_traj] if xd0.ndim == 2 else np.broadcast_to(xd0, (self.n_traj, xd0.size))
+                object.__setattr__(self, "_xd_full", cs - np.repeat(base, cnt, axis=0) + np.repeat(x0, cnt, axis=0))
+            return self._xd_full
+        raise AttributeError(name)
 
     def __len__(self):
         return self.n_traj
 
     def __getitem__(self, i) -> PDMPResult:
         a, b = int(self.offsets[i]), int(self.offsets[i + 1])
+        if self.__dict__.get("_event") is not None and self._xd_full is None:
+            # event transport: this trajectory's xd = xd0 + prefix sum of the nu rows of its reaction indices
+            xd_i = self._event_xd0(i)[None, :] + np.cumsum(self._event[0][self._xd_raw[a:b]], axis=0)
+        else:
+            xd_i = self.xd[a:b]
         # PDMPResult.rates (src/utils.jl:69, filled by save_rate: src/chvdiffeq.jl:54, src/rejectiondiffeq.jl:134): one
         # entry per saved jump after the initial slot, which the reference leaves uninitialised (resize!, src/problem.jl:158)
         rates = np.empty(0)
@@ -120,7 +153,7 @@ class EnsembleResult:
             rates = self.rate[a:b]
             if b > a and np.isnan(rates[-1]) and b - a > 1:
                 rates = rates[:-1]            # the final point at tf has no rate entry in the reference
-        return PDMPResult(self.time[a:b], self.xc[a:b].T, self.xd[a:b].T.astype(np.int64, copy=False), rates,
+        return PDMPResult(self.time[a:b], self.xc[a:b].T, xd_i.T.astype(np.int64, copy=False), rates,
                           self.save_positions, int(self.njumps[i]), int(self.nrejected[i]),
                           int(self.status[i]))
 

@@ -51,9 +51,13 @@ def solve(problem, alg, *, trajectories=1, **kw):
     try:
         _lib.check(rc)
         return _marshal.to_numpy(res, copy=True, save_positions=args["save_positions"],
-                                 sample_times=args.get("sample_times"))
+                                 sample_times=args.get("sample_times"), event=_event_tables(keep))
     finally:
         L.pdmp_result_free(C.byref(res))
+
+
+def _event_tables(keep):
+    return next((k for k in keep if isinstance(k, dict) and "event_nu" in k), None)
 
 
 class Ensemble:
@@ -120,13 +124,15 @@ class Ensemble:
                                                int(bool(records)), C.byref(res))
         _lib.check(rc)
         return _marshal.to_numpy(res, copy=copy, save_positions=self._args["save_positions"],
-                                 sample_times=self._args.get("sample_times"), keep=self, records=records)
+                                 sample_times=self._args.get("sample_times"), keep=self, records=records,
+                                 event=_event_tables(self._keep))
 
     def fetch(self, records=True, copy=False):
         res = _abi.Result()
         _lib.check(_lib.lib().pdmp_ensemble_fetch(self._h, int(bool(records)), C.byref(res)))
         return _marshal.to_numpy(res, copy=copy, save_positions=self._args["save_positions"],
-                                 sample_times=self._args.get("sample_times"), keep=self, records=records)
+                                 sample_times=self._args.get("sample_times"), keep=self, records=records,
+                                 event=_event_tables(self._keep))
 
     def counters(self):
         res = _abi.Result()

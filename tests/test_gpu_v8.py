@@ -319,3 +319,47 @@ def test_statistics_chunked_and_multi_device(G, monkeypatch):
     dev = G.solve(pb, G.CHVGPU("tcp"), devices=[0, 0, 0], **kw)
     assert np.array_equal(dev.batch_count, one.batch_count) and np.allclose(dev.batch_sum, one.batch_sum, rtol=1e-12, atol=1e-12)
     assert np.allclose(dev.mean(), one.mean(), rtol=1e-12) and np.allclose(dev.var(), one.var(), rtol=1e-10)
+
+
+# ---- event transport: ONE byte of discrete state per saved point (xd_bytes = 1) -----------------------------
+@pytest.mark.parametrize("model,alg,tf,nj,sp", [("tcp", "chv", 50.0, 300, (False, True)), ("morris_lecar", "chv", 30.0, 200, (True, True)),
+                                                ("sir_rejection", "rejection", 150.0, 1000, (False, True)),
+                                                ("tcp2d", "chv", 10.0, 300, (True, False))])
+def test_event_transport_rebuilds_xd_exactly(G, model, alg, tf, nj, sp):
+    """The wire carries the index of the reaction behind every saved point instead of xd (TCP: 20 -> 17 bytes per
+    point); the bindings rebuild xd as xd0 + a prefix sum of nu rows.  Must equal the int64 transport bit for bit,
+    through the one-shot call, the chunked host pipeline, per-trajectory initial conditions and device shards."""
+    pb = G.models.problem(model)
+    pb.tspan[1] = tf
+    n = 3000
+    A = G.CHVGPU(model) if alg == "chv" else G.RejectionGPU(model)
+    xd0 = np.tile(pb.xd0, (n, 1)); xd0[:, 0] += np.arange(n) % 3
+    for extra in (dict(), dict(xd0=xd0), dict(devices=[0, 0])):
+        kw = dict(trajectories=n, n_jumps=nj, seed=9, save_positions=sp, **extra)
+        full = G.solve(pb, A, **kw)
+        ev = G.solve(pb, A, xd_transport="event", **kw)
+        assert ev._xd_raw.dtype == np.uint8 and ev._xd_raw.shape == full.time.shape and ev._xd_raw.max() <= pb.n_r
+        for i in (0, 1, n // 2, n - 1):                        # per-trajectory access does not materialise the whole array
+            assert np.array_equal(ev[i].xd, full[i].xd) and np.array_equal(ev[i].time, full[i].time)
+        assert ev._xd_full is None
+        assert np.array_equal(ev.xd, full.xd) and np.array_equal(ev.xc, full.xc) and np.array_equal(ev.offsets, full.offsets)
+    # "auto" picks it when it is provably exact, and the resident handle carries the decoding tables
+    ens = G.Ensemble(pb, A, trajectories=n, n_jumps=nj, seed=9, save_positions=sp, xd_transport="auto")
+    r = ens.run_host(seed=9, copy=True)
+    assert r._event is not None and np.array_equal(r.xd, G.solve(pb, A, trajectories=n, n_jumps=nj, seed=9, save_positions=sp).xd)
+    ens.close()
+
+
+def test_event_transport_is_refused_when_not_exact(G):
+    eva = G.models.problem("neuron_eva")                           # a Delta acts after nu
+    with pytest.raises(ValueError):
+        G.solve(eva, G.CHVGPU("neuron_eva"), trajectories=4, n_jumps=50, xd_transport="event")
+    d, o, keep = G._marshal.build(eva, G.model_info("neuron_eva"), algorithm="chv", trajectories=4, n_jumps=50)
+    o.xd_bytes = 1                                                 # bypassing the binding: the library refuses too
+    import ctypes as C
+    res = G._abi.Result()
+    assert G._lib.lib().pdmp_solve_ensemble(C.byref(d), C.byref(o), C.byref(res)) == G._abi.ERR_UNSUPPORTED
+    pb = G.models.problem("tcp", tspan=(0.0, 5.0))
+    d, o, keep = G._marshal.build(pb, G.model_info("tcp"), algorithm="chv", trajectories=4, n_jumps=2 ** 23 + 2, no_records=True)
+    o.xd_bytes = 1
+    assert G._lib.lib().pdmp_solve_ensemble(C.byref(d), C.byref(o), C.byref(res)) == G._abi.ERR_UNSUPPORTED

@@ -117,10 +117,17 @@ def test_marshal_transport_rate_kind_and_save_counts(P):
     kw = dict(algorithm="chv", trajectories=4)
     _, o, _ = _marshal.build(pb, info(1, 2, 2), n_jumps=1000, **kw)
     assert o.xd_bytes == 8                                           # default: the reference's Int64 layout
-    _, o, _ = _marshal.build(pb, info(1, 2, 2), n_jumps=1000, xd_transport="auto", **kw)
-    assert o.xd_bytes == 2                                           # |xd| <= 1 + 999
-    _, o, _ = _marshal.build(pb, info(1, 2, 2), n_jumps=40000, xd_transport="auto", **kw)
+    _, o, keep = _marshal.build(pb, info(1, 2, 2), n_jumps=1000, xd_transport="auto", **kw)
+    assert o.xd_bytes == 1                                           # event transport: no Delta, |xd| <= 1 + 999 < 2^23
+    assert any(isinstance(k, dict) and "event_nu" in k for k in keep)   # the decoding tables travel with the call
+    _, o, _ = _marshal.build(pb, info(1, 2, 2), n_jumps=1000, xd_transport="auto", ind_save_d=[0], **kw)
+    assert o.xd_bytes == 2                                           # a component mask: int16 (|xd| <= 1 + 999)
+    _, o, _ = _marshal.build(pb, info(1, 2, 2), n_jumps=40000, xd_transport="auto", ind_save_d=[0], **kw)
     assert o.xd_bytes == 4                                           # 40000 jumps could overflow int16
+    _, o, _ = _marshal.build(pb, info(1, 2, 2), n_jumps=2 ** 24, xd_transport="auto", no_records=True, **kw)
+    assert o.xd_bytes == 4                                           # beyond 2^23: no event transport either
+    with pytest.raises(ValueError):
+        _marshal.build(pb, info(1, 2, 2, has_delta=1), n_jumps=10, xd_transport="event", **kw)
     _, o, _ = _marshal.build(pb, info(1, 2, 2, has_delta=1), n_jumps=10, xd_transport="auto", **kw)
     assert o.xd_bytes == 4                                           # a Delta may move xd arbitrarily
     with pytest.raises(ValueError):
