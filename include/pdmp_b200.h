@@ -180,8 +180,9 @@ typedef struct pdmp_solve_opts {
                                      1: event transport — ONE byte per saved point: the index (1-based) of
                                         the reaction that changed xd since the trajectory's previous saved
                                         point, 0 for none (initial / final / pre-jump points).  xd is rebuilt
-                                        by the bindings as xd0 + a prefix sum of nu rows.  Only for models
-                                        without a Delta and |xd0| + (n_jumps - 1) max|nu| < 2^23 (checked by
+                                        by the bindings as xd0 + a prefix sum of nu rows.  Only with post-jump
+                                        saving (save_post), for models without a Delta and
+                                        |xd0| + (n_jumps - 1) max|nu| < 2^23 (checked by
                                         the library: PDMP_ERR_UNSUPPORTED otherwise).
                                      Narrow transport cuts the device->host bytes per saved
                                      point; the bindings widen per trajectory on access.    */

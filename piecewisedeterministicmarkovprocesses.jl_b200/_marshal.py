@@ -116,10 +116,11 @@ def build(problem, info, *, algorithm, ode="dp5", trajectories=1, traj_id_offset
     o.ref_quirks = int(bool(ref_quirks))
     bound = int(np.max(np.abs(xd), initial=0)) + max(int(n_jumps) - 1, 0) * int(np.max(np.abs(nu), initial=0))
     if xd_transport == "auto":
-        xd_transport = "int32" if info.has_delta else ("event" if (bound < 2 ** 23 and ind_save_d is None) else
+        xd_transport = "int32" if info.has_delta else ("event" if (bound < 2 ** 23 and ind_save_d is None and save_positions[1]) else
                                                         "int16" if bound < 32768 else "int32")
-    if xd_transport == "event" and (bound >= 2 ** 23 or info.has_delta or ind_save_d is not None):
-        raise ValueError("xd_transport='event' needs a model without a Delta, all of xd saved and |xd| < 2^23 (bound %d)" % bound)
+    if xd_transport == "event" and (bound >= 2 ** 23 or info.has_delta or ind_save_d is not None or not save_positions[1]):
+        raise ValueError("xd_transport='event' needs a model without a Delta, post-jump saving, all of xd saved and "
+                         "|xd| < 2^23 (bound %d)" % bound)
     if xd_transport == "int16" and (bound >= 32768 or info.has_delta):
         raise ValueError("xd_transport='int16' is not provably exact for this problem (bound %d)" % bound)
     o.xd_bytes = {"int64": 8, "int32": 4, "int16": 2, "event": 1}[xd_transport]

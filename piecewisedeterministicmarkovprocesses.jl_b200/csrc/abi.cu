@@ -402,8 +402,9 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
     if (o->rng_mode == PDMP_RNG_REPLAY && (!o->replay_u || !o->replay_stride)) return fail(PDMP_ERR_INVALID, "replay_u");
     if (o->xd_bytes != 0 && o->xd_bytes != 8 && o->xd_bytes != 4 && o->xd_bytes != 2 && o->xd_bytes != 1)
         return fail(PDMP_ERR_INVALID, "xd_bytes must be 0, 8, 4, 2 or 1");
-    if (o->xd_bytes == 1 && (m.info.has_delta || o->save_d_mask))
-        return fail(PDMP_ERR_UNSUPPORTED, "xd_bytes = 1 (event transport) needs xd to change through nu alone (no Delta) and all of xd saved");
+    if (o->xd_bytes == 1 && (m.info.has_delta || o->save_d_mask || !o->save_post))
+        return fail(PDMP_ERR_UNSUPPORTED, "xd_bytes = 1 (event transport) needs xd to change through nu alone (no Delta), every jump "
+                                          "saved (save_positions[2]) and all of xd saved");
     if (o->hist_n < 0 || o->hist_n > MAXH) return fail(PDMP_ERR_INVALID, "hist_n must be <= 4");
     if (o->hist_n && o->hist_bins < 1) return fail(PDMP_ERR_INVALID, "hist_bins");
     if (d->n_traj > 0xfffffff0ull) return fail(PDMP_ERR_INVALID, "n_traj per call must be < 2^32");

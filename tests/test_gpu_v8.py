@@ -324,7 +324,7 @@ def test_statistics_chunked_and_multi_device(G, monkeypatch):
 # ---- event transport: ONE byte of discrete state per saved point (xd_bytes = 1) -----------------------------
 @pytest.mark.parametrize("model,alg,tf,nj,sp", [("tcp", "chv", 50.0, 300, (False, True)), ("morris_lecar", "chv", 30.0, 200, (True, True)),
                                                 ("sir_rejection", "rejection", 150.0, 1000, (False, True)),
-                                                ("tcp2d", "chv", 10.0, 300, (True, False))])
+                                                ("tcp2d", "chv", 10.0, 300, (True, True))])
 def test_event_transport_rebuilds_xd_exactly(G, model, alg, tf, nj, sp):
     """The wire carries the index of the reaction behind every saved point instead of xd (TCP: 20 -> 17 bytes per
     point); the bindings rebuild xd as xd0 + a prefix sum of nu rows.  Must equal the int64 transport bit for bit,
@@ -351,6 +351,11 @@ def test_event_transport_rebuilds_xd_exactly(G, model, alg, tf, nj, sp):
 
 
 def test_event_transport_is_refused_when_not_exact(G):
+    p2 = G.models.problem("tcp2d", tspan=(0.0, 5.0))              # without post-jump saving a point may sit several jumps after the last
+    with pytest.raises(ValueError):
+        G.solve(p2, G.CHVGPU("tcp2d"), trajectories=4, n_jumps=50, save_positions=(True, False), xd_transport="event")
+    r = G.solve(p2, G.CHVGPU("tcp2d"), trajectories=4, n_jumps=50, save_positions=(True, False), xd_transport="auto")
+    assert r._event is None and r.xd.dtype == np.int16
     eva = G.models.problem("neuron_eva")                           # a Delta acts after nu
     with pytest.raises(ValueError):
         G.solve(eva, G.CHVGPU("neuron_eva"), trajectories=4, n_jumps=50, xd_transport="event")
