@@ -565,7 +565,9 @@ struct MinBlocks {
 };
 
 // lane states of the phase scheduler
-enum { LANE_DEAD = 0, LANE_RUN = 1, LANE_WAIT = 2, LANE_EXHAUSTED = 3 };
+// (LANE_FAIL + status: the RK phase found the trajectory dead — non-finite state, attempt budget — and leaves
+//  the once-per-trajectory exit to the threshold phase, so that none of its code sits in the RK loop)
+enum { LANE_DEAD = 0, LANE_RUN = 1, LANE_EXHAUSTED = 2, LANE_WAIT = 3, LANE_FAIL = 4 };
 
 // default scheduler thresholds; a model may define `static constexpr int SCHED_JUMP, SCHED_REFILL`
 template <class M, class = void> struct SchedDefaults { static constexpr int jump = 12, refill = 2; };
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
     // per-model defaults SchedDefaults<M> (measured sweeps: profiles/r1_sched_sweep.txt).
     for (;;) {
         const unsigned m_run = __ballot_sync(0xffffffffu, st == LANE_RUN);
-        const unsigned m_wait = __ballot_sync(0xffffffffu, st == LANE_WAIT);
+        const unsigned m_wait = __ballot_sync(0xffffffffu, st >= LANE_WAIT);
         const unsigned m_dead = __ballot_sync(0xffffffffu, st == LANE_DEAD);
         if (!(m_run | m_wait | m_dead)) break;
         const int n_run = __popc(m_run), n_wait = __popc(m_wait), n_dead = __popc(m_dead);
@@ -638,8 +640,9 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
                     if (due) fc = tr.pre_sample(P, c_aux);
                 }
             }
-            if (st == LANE_WAIT) {
+            if (st >= LANE_WAIT) {
                 bool done;
+                if (st > LANE_WAIT) fc = st - LANE_FAIL;     // failed in the RK phase
                 if (fc) { tr.finish(P, fc); done = true; }
                 else if (!NO_FLOW && tr.r != 0.0) done = false;   // stopped for a sample only: back to stepping
                 else {
@@ -660,10 +663,12 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
         // (compiled out when there is no flow: its registers would cap the occupancy of a kernel that
         //  only ever runs the candidate section)
         if constexpr (!NO_FLOW) {
-        const int not_run0 = 32 - n_run;
         const int thr = P.jump_thresh > 0 ? min(P.jump_thresh, (n_live + 1) >> 1) : 1;
+        // the phase ends when enough lanes wait for the threshold section (or none runs): one ballot per attempt
+        const int run_floor = max(n_run - max(thr - n_wait, 1), 0);
         // OrdinaryDiffEq snaps to a tstop that is within 100 eps of the step's end
         const double snaptol = 2.220446049250313e-14 * fabs(tr.tstop);
+        const bool pol1 = P.tstop_policy == 1;
         for (;;) {
         if (st == LANE_RUN) {
             const double hprop = tr.h;
@@ -689,13 +694,10 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
                 double hnext = step * (double)tr.pi.template accept<D>((float)e2);
                 const double r2 = tr.r - step;
                 // threshold reached: exactly (clipped step) or within 100 eps (the floating-point snap)
-                if (clipped || r2 < snaptol) {
-                    tr.r = 0.0;
-                    st = LANE_WAIT;
-                    if (clipped && P.tstop_policy == 1 && hnext < hprop) hnext = hprop;
-                } else {
-                    tr.r = r2;
-                }
+                const bool land = clipped || r2 < snaptol;
+                tr.r = land ? 0.0 : r2;
+                if (land) st = LANE_WAIT;
+                if (pol1 && clipped && hnext < hprop) hnext = hprop;
                 tr.h = hnext;
                 if constexpr (STATS && !ConstFlow<M>::value) if (tr.sample_due(P)) st = LANE_WAIT;   // stepped past a sample time
             } else {
@@ -711,14 +713,13 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
                     for (int i = 0; i < D; ++i) ok = ok && isfinite(tr.y[i]) && isfinite(tr.k1[ChvSigned<M>::value ? D - 1 : i]);
                     tr.h = 0.2 * step;
                     const double sv = tr.svar();
-                    if (!ok || !(sv + tr.h > sv)) { tr.finish(P, PDMP_ST_NAN); st = LANE_DEAD; c_attempts += tr.attempts; }
+                    if (!ok || !(sv + tr.h > sv)) st = LANE_FAIL + PDMP_ST_NAN;
                 }
             }
             // OrdinaryDiffEq's maxiters: the budget is spent and the threshold is still ahead
-            if (st == LANE_RUN && tr.attempts >= budget) { tr.finish(P, PDMP_ST_MAX_ATTEMPTS); st = LANE_DEAD; c_attempts += tr.attempts; }
+            if (st == LANE_RUN && tr.attempts >= budget) st = LANE_FAIL + PDMP_ST_MAX_ATTEMPTS;
         }
-        const int left = __popc(__ballot_sync(0xffffffffu, st != LANE_RUN)) - not_run0;   // lanes that landed (or failed)
-        if (n_wait + left >= thr || left == n_run) break;
+        if (__popc(__ballot_sync(0xffffffffu, st == LANE_RUN)) <= run_floor) break;
         }
         }
     }

@@ -37,8 +37,11 @@ if model == "neuron_mf":
         print(model, n, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in c.items()},
               "jumps/s", c["total_jumps"] / (c["kernel_ms"] * 1e-3), "candidates/s", c["total_candidates"] / (c["kernel_ms"] * 1e-3))
     sys.exit(0)
+import time
 for seed in (0, 1):
+    t0 = time.perf_counter()
     ens.run(seed=seed)
     c = ens.counters()
+    c["step_wall_ms"] = round(1e3 * (time.perf_counter() - t0), 3)
     print(model, n, "JT", os.environ.get("PDMP_JUMP_THRESH"), "RT", os.environ.get("PDMP_REFILL_THRESH"), "pol", pol, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in c.items()},
           "jumps/s", c["total_jumps"] / (c["kernel_ms"] * 1e-3))
