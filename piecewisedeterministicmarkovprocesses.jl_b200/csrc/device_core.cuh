@@ -189,6 +189,23 @@ struct DrawStream {
         if (k & 1u) { u0 = cache; u1 = a; cache = b; }
         else { u0 = a; u1 = b; }
     }
+    // The same for a stream position that is KNOWN to be odd (a CHV trajectory has consumed 1 + 2 j draws at
+    // its j-th threshold): the cached half, then the first half of a new block — no parity selects.
+    PDMP_DEV void next2_odd(int rng_mode, const double* __restrict__ replay, uint64_t replay_len, uint64_t gid,
+                            const PhiloxKeys& keys, bool& exhausted, double& u0, double& u1) {
+        const uint32_t k = idx;
+        idx += 2;
+        if (rng_mode == 1) {
+            if (k + 1 >= replay_len) { exhausted = true; u0 = u1 = 0.5; return; }
+            u0 = __ldg(replay + k); u1 = __ldg(replay + k + 1);
+            return;
+        }
+        uint32_t c0 = (uint32_t)gid, c1 = (uint32_t)(gid >> 32), c2 = (k + 1u) >> 1, c3 = 0u;
+        philox4x32_10(c0, c1, c2, c3, keys);
+        u0 = cache;
+        u1 = u01_from_bits(c0, c1);
+        cache = u01_from_bits(c2, c3);
+    }
 };
 
 // ---------------------------------------------------------------------------------------

@@ -457,10 +457,10 @@ struct Traj {
                 finish(P, PDMP_ST_NONPOSITIVE_RATE); return true;
             }
             // rand() of pfsample then rand() of :71 = the cached half of the previous Philox block and the
-            // first half of a new one: ONE Philox call, no parity branch (DrawStream::next2)
+            // first half of a new one: ONE Philox call, no parity branch (DrawStream::next2_odd)
             double u_ev;
-            rng.next2(P.rng_mode, P.replay_u + (size_t)lid * P.replay_stride, P.replay_stride, P.traj_id_offset + lid, P.keys,
-                      ex, u_ev, u_exp);
+            rng.next2_odd(P.rng_mode, P.replay_u + (size_t)lid * P.replay_stride, P.replay_stride, P.traj_id_offset + lid, P.keys,
+                          ex, u_ev, u_exp);
             // pfsample, reference src/utils.jl:46-57 (strict <, last index absorbs round-off)
             const R thr = (R)u_ev * tot;
             int ev = 1;
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
                 bool done;
                 if (st > LANE_WAIT) fc = st - LANE_FAIL;     // failed in the RK phase
                 if (fc) { tr.finish(P, fc); done = true; }
-                else if (!NO_FLOW && tr.r != 0.0) done = false;   // stopped for a sample only: back to stepping
+                else if (!NO_FLOW && STATS && !ConstFlow<M>::value && tr.r != 0.0) done = false;   // stopped for a sample only: back to stepping
                 else {
                     ++c_cands;
                     if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, c_aux, c_jumps);

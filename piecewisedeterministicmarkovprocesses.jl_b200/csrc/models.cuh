@@ -77,7 +77,7 @@ struct Tcp2dDev {  // examples/tcp2d.jl:4-25
 
 struct MorrisLecarDev {  // examples/morris_lecar.jl:8-28
     static constexpr int NC = 1, ND = 4, NR = 4, NP = 15;
-    static constexpr bool HAS_BOUND = false, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;
+    static constexpr bool HAS_BOUND = false, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = true;
     static constexpr const char* NAME = "morris_lecar";
     static constexpr int SCHED_JUMP = 6, SCHED_REFILL = 2;    // ~2 expensive RK attempts (18 exp) per jump
     enum { v_Na, g_Na, v_K, g_K, v_L, g_L, I_app, gamma_na, k_na, beta_na, gamma_k, k_k, beta_k, M, N };
@@ -98,6 +98,23 @@ struct MorrisLecarDev {  // examples/morris_lecar.jl:8-28
     }
     template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(0); }
     template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
+    // The CHV field (F, 1) / Rtot with the total rate written for the integrator: the two potassium rates are
+    // beta_k exp(+-(gamma_k v + k_k)), so ONE exponential and its reciprocal serve both (2 exp per stage instead
+    // of 3; the value differs from the three-exponential sum in the last bits only).  The rates used for the
+    // categorical draw at a jump (`rates` above) keep the reference's three separate exponentials.
+    template <class R> PDMP_DEV static void chv_field(R* dy, const R* y, const int* xd, const double* p) {
+        const R v = y[0];
+        const R e_na = exp(R(4) * R(p[gamma_na]) * v + R(4) * R(p[k_na]));
+        const R e_k = exp(R(p[gamma_k]) * v + R(p[k_k]));
+        const R e_ki = rcp_fast(e_k);
+        const R tot = ((R(p[beta_na]) * e_na * (R)xd[0] + R(p[beta_na]) * (R)xd[1]) + R(p[beta_k]) * e_k * (R)xd[2]) +
+                      R(p[beta_k]) * e_ki * (R)xd[3];
+        const R inv = rcp_fast(tot);
+        R f[1];
+        F(f, y, xd, p, y[1]);
+        dy[0] = f[0] * inv;
+        dy[1] = inv;
+    }
 };
 
 template <bool REJ>

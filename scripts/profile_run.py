@@ -27,7 +27,8 @@ elif model == "tcp2d":
                      sample_times=list(10.0 * np.arange(1, 17) / 16), hist=[(0, 0.0, 4.0), (1, 0.0, 4.0)], hist_bins=256, **tol)
 elif model == "sir_rejection":
     pb = P.models.problem("sir_rejection")
-    ens = P.Ensemble(pb, P.RejectionGPU("sir_rejection"), trajectories=n, n_jumps=1000, max_records=n * 260)
+    ens = P.Ensemble(pb, P.RejectionGPU("sir_rejection"), trajectories=n, n_jumps=1000, max_records=n * 260,
+                     save_rate=bool(int(os.environ.get("PDMP_SAVE_RATE", "0"))))
 if model == "neuron_mf":
     # RejectionExact (one warp per trajectory): one-shot solves, no resident handle
     pb = P.models.problem("neuron_mf")

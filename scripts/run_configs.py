@@ -8,7 +8,7 @@ ensemble moments against a CPU ensemble within 99 % confidence intervals).
     python -m torch.distributed.run --nproc-per-node 8 ... scripts/run_configs.py     (sharded)
 
 bench.py is the headline (C2) benchmark; this script is the evidence for the other configs
-(profiles/r1_configs_*.jsonl).  The oracle is used here only as the checker.
+(profiles/r*_configs_*.jsonl).  The oracle is used here only as the checker.
 """
 import argparse
 import json
@@ -124,13 +124,15 @@ def main():
     if want("C3"):
         n = int(1_000_000 * S)
         out, _ = throughput("C3", "morris_lecar", P.CHVGPU("morris_lecar"), n, problem=P.models.problem("morris_lecar"),
-                            n_jumps=2200, max_records=int(n / world * 760) + 4096, sample_times=[87.5, 175.0, 262.5, 350.0])
+                            n_jumps=2200, max_records=int(n / world * 760) + 4096, sample_times=[87.5, 175.0, 262.5, 350.0],
+                            xd_transport="auto")
         emit(out)
     # ---- C4: SIR rejection, 1e7 trajectories ----------------------------------------------------
     if want("C4"):
         n = int(10_000_000 * S)
         out, _ = throughput("C4", "sir_rejection", P.RejectionGPU("sir_rejection"), n, problem=P.models.problem("sir_rejection"),
-                            n_jumps=1000, max_records=int(n / world * 200) + 4096, sample_times=[50.0, 100.0, 150.0])
+                            n_jumps=1000, max_records=int(n / world * 200) + 4096, sample_times=[50.0, 100.0, 150.0],
+                            xd_transport="auto", save_rate=False)   # (the reference's Rejection default save_rate = true adds a column)
         out["note"] = "BOUND_VIOLATED trajectories are the reference's AssertionError (src/rejectiondiffeq.jl:33): the example's bound parms[1]+3.5 is violable (SURVEY finding 0.5)"
         emit(out)
     # ---- C5: tcp2d, 1e9 trajectories sharded, statistics + histograms only ---------------------
