@@ -259,6 +259,26 @@ function _xd(res, tot::Int)
     Matrix{Int64}(unsafe_wrap(Array, Ptr{T}(res.xd), (nd, tot)))
 end
 
+# event transport (`xd_bytes = 1`): the wire carries ONE byte per saved point, the index of the reaction that changed
+# xd since the trajectory's previous saved point (0: none); xd is rebuilt as xd0 + a prefix sum of nu rows
+function _xd_event(res, tot::Int, nu::Matrix{Int64}, xd0::AbstractVecOrMat{Int64})
+    nd = size(nu, 2)
+    out = Matrix{Int64}(undef, nd, tot)
+    (res.xd == C_NULL || tot == 0) && return out
+    ev = unsafe_wrap(Array, Ptr{UInt8}(res.xd), tot)
+    offs = unsafe_wrap(Array, res.offsets, Int(res.n_traj) + 1)
+    x = Vector{Int64}(undef, nd)
+    for i in 1:Int(res.n_traj)
+        x .= xd0 isa AbstractMatrix ? view(xd0, :, Int(res.traj_begin) + i) : xd0
+        for k in Int(offs[i])+1:Int(offs[i+1])
+            e = Int(ev[k])
+            e > 0 && (x .+= view(nu, e, :))
+            out[:, k] .= x
+        end
+    end
+    out
+end
+
 # ---- solve ----------------------------------------------------------------------------------
 """
     solve(problem::PDMPProblem, algo::Union{CHVGPU, RejectionGPU}; trajectories, n_jumps, kwargs...)
@@ -295,9 +315,12 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
         error("problem shape does not match device model $(algo.model)")
     (algo isa RejectionExactGPU) == (info.exact_flow != 0) ||
         error("RejectionExactGPU needs an exact-flow device model (and only it can run one)")
-    if xd_bytes == 2   # int16 transport must be provably exact: |xd0| + (n_jumps - 1) max|nu|, and no Delta on xd
-        bound = maximum(abs, car.xd0; init = 0) + max(Int64(n_jumps) - 1, 0) * maximum(abs, nu; init = 0)
-        (bound < 32768 && info.has_delta == 0) || error("xd_bytes = 2 is not provably exact for this problem (bound $bound)")
+    if xd_bytes == 2 || xd_bytes == 1   # narrow transports must be provably exact: |xd0| + (n_jumps - 1) max|nu|, and no Delta on xd
+        bound = maximum(abs, xd0 === nothing ? car.xd0 : xd0; init = 0) + max(Int64(n_jumps) - 1, 0) * maximum(abs, nu; init = 0)
+        (bound < (xd_bytes == 2 ? 32768 : 2^23) && info.has_delta == 0) ||
+            error("xd_bytes = $xd_bytes is not provably exact for this problem (bound $bound)")
+        (xd_bytes == 2 || (save_positions[2] && ind_save_d === nothing)) ||
+            error("xd_bytes = 1 (event transport) needs post-jump saving and all of xd saved")
     end
     xc = xc0 === nothing ? Vector{Float64}(car.xc0) : Matrix{Float64}(xc0)
     xd = xd0 === nothing ? Vector{Int64}(car.xd0) : Matrix{Int64}(xd0)
@@ -345,7 +368,8 @@ function SciMLBase.solve(problem::PDMP.PDMPProblem, algo::Union{CHVGPU, Rejectio
     cat1(f) = vcat([f(b) for b in blocks]...)
     cat2(f) = hcat([f(b) for b in blocks]...)
     out = EnsembleResult(offs, cat1(b -> _copy(b.time, Int(b.total_records))),
-                         cat2(b -> _copy(b.xc, Int(res.n_c), Int(b.total_records))), cat2(b -> _xd(b, Int(b.total_records))),
+                         cat2(b -> _copy(b.xc, Int(res.n_c), Int(b.total_records))),
+                         cat2(b -> res.xd_bytes == 1 ? _xd_event(b, Int(b.total_records), nu, xd) : _xd(b, Int(b.total_records))),
                          cat1(b -> _copy(b.njumps, Int(b.n_traj))), cat1(b -> _copy(b.nrejected, Int(b.n_traj))),
                          cat1(b -> _copy(b.status, Int(b.n_traj))),
                          _copy(res.stat_count, C, T), _copy(res.stat_sum, C, T), _copy(res.stat_sumsq, C, T),

@@ -103,6 +103,11 @@ template <class M> struct ChvSigned<M, decltype((void)M::CHV_SIGNED_SCALAR)> { s
 template <class M, class = void> struct ConstFlow { static constexpr bool value = false; };
 template <class M> struct ConstFlow<M, decltype((void)M::CONST_FLOW)> { static constexpr bool value = M::CONST_FLOW; };
 
+// models that register the EXACT flow of F between jumps (`HAS_EXACT_FLOW`, `flow(x, xd, p, t, dt)`): sample times and
+// the last bit are then one closed-form evaluation instead of an adaptive sub-integration (tcp2d: x' = 1, x' = -x)
+template <class M, class = void> struct ExactFlow { static constexpr bool value = false; };
+template <class M> struct ExactFlow<M, decltype((void)M::HAS_EXACT_FLOW)> { static constexpr bool value = M::HAS_EXACT_FLOW; };
+
 // geometric segment sizes: segment k holds REC_BLOCK << (k >> 2) records (4 segments per doubling)
 __host__ __device__ inline unsigned seg_records(int k) { return (unsigned)REC_BLOCK << (k >> 2); }
 
@@ -141,8 +146,7 @@ struct Traj {
     int seg_k;
     unsigned long long wslot;  // next record slot in the pool
     bool overflow;
-    int next_sample;
-    double tnext;       // sample_times[next_sample], or +huge when none is left
+    int next_sample;    // index of the next sample time not yet recorded
 
     // ------------------------------------------------------------------------------
     PDMP_DEV double draw(const KParams& P, bool& exhausted) {
@@ -246,6 +250,13 @@ struct Traj {
             ++aux_attempts;
             return true;
         }
+        if constexpr (ExactFlow<M>::value)
+            if (!quirk) {   // (the reference-faithful last bit is by definition a loose numerical solve)
+                M::flow(x, xd, P.parms, (R)t, (R)(tau - t));
+                t = tau;
+                ++aux_attempts;
+                return true;
+            }
         const double dir = tau > t ? 1.0 : -1.0;
         double hh = tau - t;
         const R rtol = quirk ? R(1e-3) : (R)P.reltol, atol = quirk ? R(1e-6) : (R)P.abstol;
@@ -314,9 +325,10 @@ struct Traj {
     }
 
     // ---- ensemble statistics at the fixed sample times -----------------------------------
-    // A lane stops (LANE_WAIT) as soon as an accepted step carries it past the next sample time,
-    // so the sample lies within the step just taken: it is reached by flowing plain F BACKWARDS
-    // from the current state (typically one RK attempt), and the current xd is the state there.
+    // Lanes never stop for a sample time.  At the next threshold (before the jump) every sample time passed since
+    // the previous one is reached by flowing plain F BACKWARDS from the pre-jump state — xd has not changed in
+    // between — latest first, so that every leg is short: exactly for models that register their flow
+    // (ExactFlow / ConstFlow), by an adaptive sub-integration otherwise.
     // time the trajectory has reached (CHV: the time slot; Rejection: s is time)
     PDMP_DEV double svar() const { return tstop - r; }   // the integration variable (Rejection: time)
     PDMP_DEV double threshold_time() const {
@@ -326,7 +338,7 @@ struct Traj {
     }
     PDMP_DEV bool sample_due(const KParams& P) const {
         if constexpr (!STATS) return false;
-        return tnext <= threshold_time();   // sample times are <= tf by contract; +huge when none is left
+        return next_sample < P.n_sample && __ldg(P.sample_times + next_sample) <= threshold_time();   // (sample times are <= tf by contract)
     }
     PDMP_DEV int pre_sample(const KParams& P, unsigned& aux) {
         int fail = PDMP_ST_OK;
@@ -343,7 +355,6 @@ struct Traj {
                 accumulate(P, j, xb);
             }
             next_sample = last;
-            tnext = last < P.n_sample ? __ldg(P.sample_times + last) : 1.7976931348623157e308;
         }
         return fail;
     }
@@ -377,7 +388,6 @@ struct Traj {
         attempts = 0;
         nrec_stored = 0; seg_left = 0; seg_k = 0; wslot = 0; overflow = false;
         next_sample = 0;
-        tnext = (STATS && P.n_sample > 0) ? __ldg(P.sample_times) : 1.7976931348623157e308;
         pi.init();
         write_record(P, P.t0, xs);  // the initial point is always kept (resize!(..., 1))
 
@@ -644,7 +654,6 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
                 bool done;
                 if (st > LANE_WAIT) fc = st - LANE_FAIL;     // failed in the RK phase
                 if (fc) { tr.finish(P, fc); done = true; }
-                else if (!NO_FLOW && STATS && !ConstFlow<M>::value && tr.r != 0.0) done = false;   // stopped for a sample only: back to stepping
                 else {
                     ++c_cands;
                     if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, c_aux, c_jumps);
@@ -699,7 +708,6 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
                 if (land) st = LANE_WAIT;
                 if (pol1 && clipped && hnext < hprop) hnext = hprop;
                 tr.h = hnext;
-                if constexpr (STATS && !ConstFlow<M>::value) if (tr.sample_due(P)) st = LANE_WAIT;   // stepped past a sample time
             } else {
                 ++c_rejects;
                 if (e2 < (sizeof(R) == 4 ? (R)3.4028234e38f : (R)1.7976931348623157e308)) {

@@ -73,6 +73,13 @@ struct Tcp2dDev {  // examples/tcp2d.jl:4-25
     }
     template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(0); }
     template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
+    // exact flow of F over dt (either sign): one component moves at unit speed, the other decays exponentially
+    static constexpr bool HAS_EXACT_FLOW = true;
+    template <class R> PDMP_DEV static void flow(R* x, const int* xd, const double* p, R t, R dt) {
+        const R e = exp(-dt);
+        if ((xd[0] & 1) == 0) { x[0] += dt; x[1] *= e; }
+        else { x[0] *= e; x[1] += dt; }
+    }
 };
 
 struct MorrisLecarDev {  // examples/morris_lecar.jl:8-28
