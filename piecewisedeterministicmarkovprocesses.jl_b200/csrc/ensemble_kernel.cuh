@@ -566,12 +566,18 @@ struct Traj {
 #ifndef PDMP_MINB_SMALL
 #define PDMP_MINB_SMALL 8
 #endif
+#ifndef PDMP_MINB_MEDIUM
+#define PDMP_MINB_MEDIUM 5
+#endif
+#ifndef PDMP_MINB_LARGE
+#define PDMP_MINB_LARGE 4
+#endif
 template <class M, int ALG, class R>
 struct MinBlocks {
     static constexpr int D = (ALG == PDMP_ALG_CHV) ? M::NC + 1 : M::NC;
     static constexpr bool small = (D <= 2 && M::NR <= 2 && M::ND <= 2);
     static constexpr bool medium = (D <= 3 && M::NR <= 2 && M::ND <= 2);   // tcp2d: 96 registers, measured +8 %
-    static constexpr int value = sizeof(R) == 4 ? (small ? 7 : 5) : (small ? (M::HAS_CHV_FIELD ? PDMP_MINB_SMALL : 6) : medium ? 5 : 4);
+    static constexpr int value = sizeof(R) == 4 ? (small ? 7 : 5) : (small ? (M::HAS_CHV_FIELD ? PDMP_MINB_SMALL : 6) : medium ? PDMP_MINB_MEDIUM : PDMP_MINB_LARGE);
 };
 
 // lane states of the phase scheduler
@@ -639,33 +645,11 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
         }
 
         const int n_live = n_run + n_wait;
-        if (n_wait && (n_run == 0 || n_wait >= min(P.jump_thresh, (n_live + 1) >> 1))) {
-            // ---- JUMP ----
-            // sampling pass first: the few lanes whose threshold lies beyond a fixed sample time flow
-            // their anchor there; a block of its own, so that the warp is converged again for the jump pass
-            int fc = 0;
-            if constexpr (STATS) {
-                const bool due = st == LANE_WAIT && tr.sample_due(P);
-                if (__any_sync(0xffffffffu, due)) {
-                    if (due) fc = tr.pre_sample(P, c_aux);
-                }
-            }
-            if (st >= LANE_WAIT) {
-                bool done;
-                if (st > LANE_WAIT) fc = st - LANE_FAIL;     // failed in the RK phase
-                if (fc) { tr.finish(P, fc); done = true; }
-                else {
-                    ++c_cands;
-                    if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, c_aux, c_jumps);
-                    else done = tr.rej_candidate(P, c_aux, c_jumps);
-                }
-                if (done) { st = LANE_DEAD; c_attempts += tr.attempts; }
-                else if (NO_FLOW) { tr.r = 0.0; }   // F = F_dummy: next candidate directly
-                else st = LANE_RUN;
-            }
-            continue;
-        }
-
+        // Enough lanes wait (or none can run): straight to the threshold section.  Otherwise an RK phase first; it
+        // ends when enough lanes have landed, so the threshold section ALWAYS follows it — one scheduling decision
+        // per (RK, JUMP) pair instead of one per phase.
+        const bool jump_now = n_wait && (n_run == 0 || n_wait >= min(P.jump_thresh, (n_live + 1) >> 1));
+        if (!jump_now) {
         // ---- RK: adaptive attempts, clipped at the threshold (tstops), until enough lanes wait ----
         // Lanes only LEAVE the running set in this phase, so the scheduler's decision reduces to one
         // ballot per attempt; the full three-way test is redone when the threshold is reached.
@@ -729,6 +713,32 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
         }
         if (__popc(__ballot_sync(0xffffffffu, st == LANE_RUN)) <= run_floor) break;
         }
+        }
+        }
+        {
+            // ---- JUMP: the threshold section for every waiting lane (and the exit of lanes that failed in RK) ----
+            // sampling pass first: the few lanes whose threshold lies beyond a fixed sample time flow
+            // their anchor there; a block of its own, so that the warp is converged again for the jump pass
+            int fc = 0;
+            if constexpr (STATS) {
+                const bool due = st == LANE_WAIT && tr.sample_due(P);
+                if (__any_sync(0xffffffffu, due)) {
+                    if (due) fc = tr.pre_sample(P, c_aux);
+                }
+            }
+            if (st >= LANE_WAIT) {
+                bool done;
+                if (st > LANE_WAIT) fc = st - LANE_FAIL;     // failed in the RK phase
+                if (fc) { tr.finish(P, fc); done = true; }
+                else {
+                    ++c_cands;
+                    if constexpr (ALG == PDMP_ALG_CHV) done = tr.chv_threshold(P, c_aux, c_jumps);
+                    else done = tr.rej_candidate(P, c_aux, c_jumps);
+                }
+                if (done) { st = LANE_DEAD; c_attempts += tr.attempts; }
+                else if (NO_FLOW) { tr.r = 0.0; }   // F = F_dummy: next candidate directly
+                else st = LANE_RUN;
+            }
         }
     }
 
