@@ -206,23 +206,20 @@ def to_numpy(res, *, copy=True, save_positions=(False, True), sample_times=None,
 
 def _from_blocks(res, *, copy, save_positions, sample_times, keep, records, event=None):
     """Multi-device result: one block per device shard (include/pdmp_b200.h, pdmp_result.blocks).  The blocks
-    stay separate views (`out.blocks`); the flat arrays of the EnsembleResult are their concatenation
-    (a host copy), with the offsets rebased, so that `res[i]` and the whole-array properties work unchanged."""
+    stay separate views (`out.blocks`); `res[i]` goes straight to its block; the flat arrays of the EnsembleResult
+    (their concatenation, offsets rebased: a host copy of everything) are built on first access only."""
     blocks = [to_numpy(res.blocks[g], copy=copy, save_positions=save_positions, sample_times=sample_times, keep=keep,
                        records=records, event=event) for g in range(int(res.n_blocks))]
     for g, b in enumerate(blocks):
         b.shard = (int(res.blocks[g].traj_begin), b.n_traj)
         b.device = int(res.blocks[g].device)
     T, Cc, H, B = res.n_sample_times, res.n_comp, res.hist_n, res.hist_bins
-    base = np.cumsum([0] + [len(b.time) for b in blocks])
-    offsets = np.concatenate([b.offsets[:-1] + np.uint64(base[g]) for g, b in enumerate(blocks)] + [np.array([base[-1]], np.uint64)])
-    cat = lambda name: np.concatenate([getattr(b, "_xd_raw" if name == "xd" and b._event is not None else name) for b in blocks])
+    empty = np.zeros(0)
     out = EnsembleResult(
-        n_traj=int(res.n_traj), n_c=res.n_c, n_d=res.n_d, offsets=offsets, time=cat("time"), xc=cat("xc"), xd=cat("xd"),
-        njumps=cat("njumps"), nrejected=cat("nrejected"), status=cat("status"),
+        n_traj=int(res.n_traj), n_c=res.n_c, n_d=res.n_d, offsets=empty, time=empty, xc=empty, xd=empty,
+        njumps=empty, nrejected=empty, status=empty,
         stat_count=_arr(res.stat_count, (T, Cc), np.float64, True), stat_sum=_arr(res.stat_sum, (T, Cc), np.float64, True),
         stat_sumsq=_arr(res.stat_sumsq, (T, Cc), np.float64, True), hist=_arr(res.hist, (T, H, B), np.uint64, True),
-        rate=cat("rate") if blocks[0].rate is not None else None,
         stat_pivot=_arr(res.stat_pivot, (Cc,), np.float64, True) if res.batch_count else None,
         batch_count=_arr(res.batch_count, (_abi.STAT_BATCHES, T, Cc), np.float64, True) if res.batch_count else None,
         batch_sum=_arr(res.batch_sum, (_abi.STAT_BATCHES, T, Cc), np.float64, True) if res.batch_count else None,
@@ -234,6 +231,5 @@ def _from_blocks(res, *, copy, save_positions, sample_times, keep, records, even
         save_positions=tuple(bool(x) for x in save_positions),
         sample_times=None if sample_times is None else np.array(sample_times, dtype=np.float64), _keep=keep)
     out.blocks = blocks
-    if blocks[0]._event is not None:
-        out._set_event_transport(event["event_nu"], event["event_xd0"], 0)
+    out._defer_flat_arrays()      # offsets / time / xc / xd / ... = concatenation of the blocks, on first access
     return out

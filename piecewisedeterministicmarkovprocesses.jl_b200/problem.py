@@ -122,8 +122,33 @@ class EnsembleResult:
         nu_ext, xd0, begin = self._event
         return xd0[begin + i] if xd0.ndim == 2 else xd0
 
+    _FLAT = ("offsets", "time", "xc", "xd", "njumps", "nrejected", "status", "rate")
+
+    def _defer_flat_arrays(self):
+        """Multi-device result: the flat arrays are the concatenation of the blocks' (a host copy of everything): built on
+        first access only, one attribute at a time — `res[i]`, the counters and the statistics never need them."""
+        for name in self._FLAT:
+            self.__dict__.pop(name, None)
+        object.__setattr__(self, "_block_begin", np.cumsum([0] + [b.n_traj for b in self.blocks]))
+
+    def _concat(self, name):
+        bl = self.blocks
+        if name == "offsets":
+            base = np.cumsum([0] + [int(b.offsets[-1]) for b in bl])
+            return np.concatenate([b.offsets[:-1] + np.uint64(base[g]) for g, b in enumerate(bl)] + [np.array([base[-1]], np.uint64)])
+        if name == "rate" and bl[0].rate is None:
+            return None
+        if name == "xd" and bl[0].__dict__.get("_event") is not None:
+            return np.concatenate([b.xd for b in bl])            # every block rebuilds its own xd from its reaction indices
+        return np.concatenate([getattr(b, name) for b in bl])
+
     def __getattr__(self, name):
-        # only reached for attributes that are not set: `xd` under the event transport
+        # only reached for attributes that are not set: the deferred flat arrays of a multi-device result, and `xd`
+        # under the event transport
+        if name in EnsembleResult._FLAT and self.__dict__.get("blocks") and "_block_begin" in self.__dict__:
+            v = self._concat(name)
+            object.__setattr__(self, name, v)
+            return v
         if name == "xd" and self.__dict__.get("_event") is not None:
             if self._xd_full is None:
                 nu_ext, xd0, begin = self._event
@@ -140,6 +165,10 @@ class EnsembleResult:
         return self.n_traj
 
     def __getitem__(self, i) -> PDMPResult:
+        if self.__dict__.get("blocks") and "_block_begin" in self.__dict__:      # multi-device: straight to the block
+            i = int(i) + (self.n_traj if i < 0 else 0)
+            g = int(np.searchsorted(self._block_begin, i, side="right")) - 1
+            return self.blocks[g][i - int(self._block_begin[g])]
         a, b = int(self.offsets[i]), int(self.offsets[i + 1])
         if self.__dict__.get("_event") is not None and self._xd_full is None:
             # event transport: this trajectory's xd = xd0 + prefix sum of the nu rows of its reaction indices
@@ -195,5 +224,8 @@ class EnsembleResult:
         return np.nanstd(self.batch_vars(), axis=0, ddof=1) / np.sqrt(np.sum(self.batch_count > 1, axis=0))
 
     def status_histogram(self):
-        c = np.bincount(self.status, minlength=len(_abi.STATUS_NAMES))
+        if self.__dict__.get("blocks") and "status" not in self.__dict__:
+            c = sum(np.bincount(b.status, minlength=len(_abi.STATUS_NAMES)) for b in self.blocks)
+        else:
+            c = np.bincount(self.status, minlength=len(_abi.STATUS_NAMES))
         return {name: int(c[k]) for k, name in enumerate(_abi.STATUS_NAMES) if c[k]}
