@@ -487,6 +487,8 @@ int32_t pdmp_ensemble_create(const pdmp_problem_desc* d, const pdmp_solve_opts* 
         const char* ej = std::getenv("PDMP_JUMP_THRESH");
         const char* er = std::getenv("PDMP_REFILL_THRESH");
         P.jump_thresh = ej ? std::max(1, std::atoi(ej)) : m.sched_jump;
+        const char* ec = std::getenv("PDMP_JUMP_CAP");
+        P.jump_cap_q = ec ? std::min(4, std::max(1, std::atoi(ec))) : 2;
         P.refill_thresh = er ? std::max(1, std::atoi(er)) : m.sched_refill;
     }
     P.n_sample = o->n_sample_times; P.n_comp = NC + ND;

@@ -44,6 +44,7 @@ struct KParams {
     long long n_jumps, max_attempts;
     int save_pre, save_post, tstop_policy, rng_mode;
     int jump_thresh, refill_thresh;  // phase scheduler: lanes that must wait before JUMP / REFILL run
+    int jump_cap_q;                  // ... and the cap on jump_thresh as quarters of the live lanes (2: half)
     unsigned long long seed;
     PhiloxKeys keys;                 // round keys of `seed` (philox_round_keys)
     const double* replay_u;
@@ -648,7 +649,8 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
         // Enough lanes wait (or none can run): straight to the threshold section.  Otherwise an RK phase first; it
         // ends when enough lanes have landed, so the threshold section ALWAYS follows it — one scheduling decision
         // per (RK, JUMP) pair instead of one per phase.
-        const bool jump_now = n_wait && (n_run == 0 || n_wait >= min(P.jump_thresh, (n_live + 1) >> 1));
+        const int jcap = (n_live * P.jump_cap_q + 3) >> 2;
+        const bool jump_now = n_wait && (n_run == 0 || n_wait >= min(P.jump_thresh, jcap));
         if (!jump_now) {
         // ---- RK: adaptive attempts, clipped at the threshold (tstops), until enough lanes wait ----
         // Lanes only LEAVE the running set in this phase, so the scheduler's decision reduces to one
@@ -656,7 +658,7 @@ __global__ void __launch_bounds__(BLOCK, MinBlocks<M, ALG, R>::value) ensemble_k
         // (compiled out when there is no flow: its registers would cap the occupancy of a kernel that
         //  only ever runs the candidate section)
         if constexpr (!NO_FLOW) {
-        const int thr = P.jump_thresh > 0 ? min(P.jump_thresh, (n_live + 1) >> 1) : 1;
+        const int thr = P.jump_thresh > 0 ? min(P.jump_thresh, jcap) : 1;
         // the phase ends when enough lanes wait for the threshold section (or none runs): one ballot per attempt
         const int run_floor = max(n_run - max(thr - n_wait, 1), 0);
         // OrdinaryDiffEq snaps to a tstop that is within 100 eps of the step's end
