@@ -129,6 +129,9 @@ class EnsembleResult:
         first access only, one attribute at a time — `res[i]`, the counters and the statistics never need them."""
         for name in self._FLAT:
             self.__dict__.pop(name, None)
+        if self.blocks[0].__dict__.get("_event") is not None:      # event transport: the blocks hold the reaction indices
+            object.__setattr__(self, "_event", self.blocks[0]._event)
+            self.__dict__.pop("_xd_raw", None)
         object.__setattr__(self, "_block_begin", np.cumsum([0] + [b.n_traj for b in self.blocks]))
 
     def _concat(self, name):
@@ -145,7 +148,7 @@ class EnsembleResult:
     def __getattr__(self, name):
         # only reached for attributes that are not set: the deferred flat arrays of a multi-device result, and `xd`
         # under the event transport
-        if name in EnsembleResult._FLAT and self.__dict__.get("blocks") and "_block_begin" in self.__dict__:
+        if (name in EnsembleResult._FLAT or name == "_xd_raw") and self.__dict__.get("blocks") and "_block_begin" in self.__dict__:
             v = self._concat(name)
             object.__setattr__(self, name, v)
             return v
