@@ -107,9 +107,10 @@ class EnsembleResult:
     blocks: Optional[list] = None             # per-device EnsembleResults of a multi-device run
     device: int = 0
     _keep: Any = None
-    _event: Any = None            # (nu_ext [n_r + 1, n_d], xd0, first global index) under the event transport
-    _xd_raw: Any = None           # the reaction indices as shipped (uint8 [total])
-    _xd_full: Any = None
+    # set on demand (not dataclass fields, so that __getattr__ can build them lazily):
+    #   _event    (nu_ext [n_r + 1, n_d], xd0, first global index) under the event transport
+    #   _xd_raw   the reaction indices as shipped (uint8 [total])
+    #   _xd_full  xd rebuilt from them
 
     def _set_event_transport(self, nu, xd0, traj_begin):
         """xd arrived as ONE byte per saved point (the reaction index, 0 = none): keep the bytes, rebuild xd lazily."""
@@ -152,6 +153,8 @@ class EnsembleResult:
             v = self._concat(name)
             object.__setattr__(self, name, v)
             return v
+        if name in ("_event", "_xd_full") or (name == "_xd_raw" and not self.__dict__.get("blocks")):
+            return None
         if name == "xd" and self.__dict__.get("_event") is not None:
             if self._xd_full is None:
                 nu_ext, xd0, begin = self._event
