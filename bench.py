@@ -44,8 +44,8 @@ FLOPS_PER_ATTEMPT_TCP = 180.0   # D*72 + 2 + 10 + 6*C_rhs, D =
 REC_BYTES_TCP = 32.0            # 8*(1+n_c) + 8*n_d per saved point; pool record
 CSR_BYTES_TCP = 17.0            # CSR / wire record with the event transport: 8 (t) + 8 (xc) + 1 (reaction index)
 # DRAM bytes per saved record measured by `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum over the
-# records of that launch; profiles/r1_tcp_kernel_v11_full.txt, profiles/r1_compact_kernel_v11_full.txt)
-NCU_DRAM_BYTES_PER_RECORD = {"ensemble_kernel": 33.8, "compact_kernel": 50.4}
+# records of that launch; profiles/r2_tcp_kernel_final_4M_full.txt (incl. the sample rows), profiles/r2_compact_kernel_final_full.txt)
+NCU_DRAM_BYTES_PER_RECORD = {"ensemble_kernel": 34.6, "compact_kernel": 50.9}
 
 
 def workload_config(n_traj, n_gpus):

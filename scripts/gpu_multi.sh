@@ -12,3 +12,7 @@ grep -E "^\{" gpurun_out/r2_bench_n$N.log | python -c "import sys,json; d=json.l
 timeout 1200 python bench.py --gpus $N --steps 5 --warmup 3 --single-process > gpurun_out/r2_bench_sp_n$N.log 2>&1; echo "rc=$?" >> gpurun_out/r2_bench_sp_n$N.log
 grep -E "^\{" gpurun_out/r2_bench_sp_n$N.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('single-process', d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'])"
 tail -n 2 gpurun_out/r2_bench_sp_n$N.log | cut -c1-300
+if [ "$N" -ge 4 ]; then
+  timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 scripts/run_configs.py --no-parity > gpurun_out/r2_configs_n$N.jsonl 2> gpurun_out/r2_configs_n$N.err; echo "configs rc=$?"
+  cut -c1-330 gpurun_out/r2_configs_n$N.jsonl
+fi
