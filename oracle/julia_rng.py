@@ -19,7 +19,9 @@ for the oracle and for the GPU replay mode, without a Julia runtime:
 The restatement is self-validating: fed to the oracle's Rejection / CHV restatements it reproduces
 the reference's stored results [0, 26, 83] (examples/sir-rejection.jl, test/runtests.jl:64-69) and
 [0, 28, 81] (examples/sir.jl, third solve on the continuing stream, test/runtests.jl:57-62); a wrong
-seeding rule, generator or float conversion cannot hit those by chance.
+seeding rule, generator or float conversion cannot hit those by chance.  With the array form `rand(N)`
+(rand_array) it also reproduces `result.xd[1,end] == 100` of examples/neuron_rejection_exact.jl
+(test/runtests.jl:71-75: RejectionExact, second of two solves on a continuing stream).
 """
 import hashlib
 import struct
@@ -70,6 +72,33 @@ class Xoshiro:
     def rand_stream(self, n):
         """The next n scalar `rand()` values."""
         return np.array([self.rand() for _ in range(n)], dtype=np.float64)
+
+    def rand_array(self, n):
+        """`rand(n)` (Vector{Float64}), which is NOT n scalar draws: Julia 1.7 - 1.10 fill arrays of >= 64 bytes from
+        eight SIMD xoshiro256++ lanes forked off the main generator — lane state word w = MULT[w] * rand(UInt64), the
+        32 seeds drawn word by word (s0 of the 8 lanes first) — 8 values per round, lane by lane; the tail that does
+        not fill a round comes from the main generator (stdlib/Random/src/XoshiroSimd.jl: xoshiro_bulk)."""
+        mult = (0x02011ce34bce797f, 0x5a94851fb48a6e05, 0x3688cf5d48899fa7, 0x867b4bb4c42e5661)
+        out = np.empty(n, dtype=np.float64)
+        i = 0
+        if n * 8 >= 64:
+            s0, s1, s2, s3 = ([(m * self.next_u64()) & _M for _ in range(8)] for m in mult)
+            while i + 8 <= n:
+                for l in range(8):
+                    res = (_rotl((s0[l] + s3[l]) & _M, 23) + s0[l]) & _M
+                    t = (s1[l] << 17) & _M
+                    s2[l] ^= s0[l]
+                    s3[l] ^= s1[l]
+                    s1[l] ^= s2[l]
+                    s0[l] ^= s3[l]
+                    s2[l] ^= t
+                    s3[l] = _rotl(s3[l], 45)
+                    out[i + l] = (res >> 11) * 2.0 ** -53
+                i += 8
+        while i < n:
+            out[i] = self.rand()
+            i += 1
+        return out
 
 
 def stream(seed, n):

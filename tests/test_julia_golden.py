@@ -106,3 +106,73 @@ def test_xoshiro_restatement_is_stable():
     assert [again.rand() for _ in range(4)] == list(u)
     # seeds above 2^32 use two UInt32 limbs (make_seed)
     assert julia_rng.stream(2 ** 32 + 5, 2).tolist() != julia_rng.stream(5, 2).tolist()
+
+
+# ---- examples/neuron_rejection_exact.jl: RejectionExact, N = 100 neurons ---------------------------------------------
+#   Random.seed!(1234); xc0 = rand(N)*0.2 .+ 0.5          (array rand: julia_rng.Xoshiro.rand_array)
+#   Random.seed!(8); result = solve(problem, RejectionExact(); n_jumps = 10_000, ...)
+#   result = solve(problem, RejectionExact(); n_jumps = 10_000, ...)        <- the tested one, on the CONTINUING stream
+#   @test result.xd[1,end] == 100                                            (test/runtests.jl:71-75)
+# Draws of one solve (src/rejection.jl:3-91): 1 (init!) + 2 per candidate (thinning test, next exponential) + 1 per
+# executed jump (pfsample); the run ends by the n_jumps cap long before tf = 10 050, so no candidate lands on tf.
+# The stored integer is the spike count of one neuron out of 100 (values 98 ... 106 occur): a weaker pin than the SIR
+# vectors above on its own — together with them it fixes the array-rand restatement and the RejectionExact path.
+def _neuron_chain(solver, P):
+    xc0 = julia_rng.Xoshiro(1234).rand_array(100) * 0.2 + 0.5
+    pb = P.models.problem("neuron_mf", xc0=list(xc0))
+    u = julia_rng.stream(8, 1_480_000)
+    out, at = [], 0
+    for k in range(2):
+        r = solver(pb, trajectories=1, n_jumps=10_000, replay=u[None, at:], save_c_count=2, save_d_count=2)
+        assert r.status[0] == P._abi.ST_HIT_NJUMPS and int(r.njumps[0]) == 10_000
+        at += 1 + 2 * int(r.counters["total_candidates"]) + int(r.counters["total_jumps"])
+        out.append(r)
+    return out, xc0
+
+
+@pytest.mark.timeout(300)
+def test_neuron_rejection_exact_reference_golden_oracle(orc, P):
+    rs, xc0 = _neuron_chain(lambda pb, **kw: orc.solve(pb, "neuron_mf", algorithm="rejection_exact", **kw), P)
+    assert 0.5 <= xc0.min() and xc0.max() < 0.7
+    assert int(rs[1][0].xd[0, -1]) == 100           # test/runtests.jl:73
+    assert int(rs[0][0].xd[0, -1]) == 98            # the first solve (not asserted by the reference)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_neuron_rejection_exact_reference_golden_gpu(P, orc):
+    rs, _ = _neuron_chain(lambda pb, **kw: P.solve(pb, P.RejectionExactGPU("neuron_mf"), **kw), P)
+    assert int(rs[1][0].xd[0, -1]) == 100           # test/runtests.jl:73
+    cs, _ = _neuron_chain(lambda pb, **kw: orc.solve(pb, "neuron_mf", algorithm="rejection_exact", **kw), P)
+    for g, c in zip(rs, cs):
+        assert np.array_equal(g.xd, c.xd) and np.array_equal(g.nrejected, c.nrejected)
+        assert np.max(np.abs(g.time - c.time)) < 1e-8
+
+
+# ---- examples/pdmp_example_eva.jl: a Delta acting on xc, a non-trivial flow ------------------------------------------
+#   Random.seed!(123); result1 = solve(problem, Rejection(:lsoda); n_jumps = 200)
+#   @test result1.time[end] == 100.   ;   @test result1.xd[2,end] == 107                  (test/runtests.jl:50-55)
+# `Rejection(:lsoda)` is the legacy loop (src/rejection.jl:3-91); it consumes the stream in the same order as the
+# DiffEq-based Rejection this engine replaces — thinning test, next exponential, then pfsample at an executed jump — and
+# visits the same candidate times t + E / bound, so with an accurate flow (F = -(x - 1.5), rates x^4) the discrete
+# outcome is the same: the stored values pin the neuron_eva functor (F, R, Delta on xc, nu) and the Rejection driver
+# with a real ODE flow in between candidates.
+def _eva(solver, P):
+    pb = P.models.problem("neuron_eva")          # xc0 = [0], xd0 = [0, 1], parms = [1.0], tspan (0, 100): the example's data
+    return solver(pb, trajectories=1, n_jumps=200, replay=julia_rng.stream(123, 4096)[None, :])
+
+
+def test_neuron_eva_reference_golden_oracle(orc, P):
+    r = _eva(lambda pb, **kw: orc.solve(pb, "neuron_eva", algorithm="rejection", ode="tsit5", **kw), P)
+    assert r[0].time[-1] == 100.0 and int(r[0].xd[1, -1]) == 107
+    assert r.status[0] == P._abi.ST_OK
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ode", ["dp5", "tsit5"])
+def test_neuron_eva_reference_golden_gpu(P, orc, ode):
+    g = _eva(lambda pb, **kw: P.solve(pb, P.RejectionGPU("neuron_eva", ode=ode), **kw), P)
+    assert g[0].time[-1] == 100.0 and int(g[0].xd[1, -1]) == 107
+    c = _eva(lambda pb, **kw: orc.solve(pb, "neuron_eva", algorithm="rejection", ode=ode, **kw), P)
+    assert np.array_equal(g.xd, c.xd) and np.array_equal(g.nrejected, c.nrejected)
+    assert np.max(np.abs(g.time - c.time)) < 1e-7 and np.max(np.abs(g.xc - c.xc)) < 1e-6
