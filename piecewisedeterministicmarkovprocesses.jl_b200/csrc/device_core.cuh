@@ -24,15 +24,23 @@ PDMP_DEV double rcp_fast(double x) {
 #ifdef PDMP_EXACT_DIV
     return 1.0 / x;
 #else
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    double e = fma(-x, r0, 1.0);
+    double r = fma(r0, e, r0);
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
+#ifdef PDMP_RCP_DIV_FALLBACK
     const double ax = fabs(x);
     if (!(ax > 1e-290 && ax < 1e290)) r = 1.0 / x;  // zero / inf / nan / denormal-range
     return r;
+#else
+    // outside 2^-959 <= |x| < 2^961 the Newton steps could overflow / produce NaN: keep the bare seed there, which is
+    // already the right answer for 0 (inf), inf (0) and NaN, and good to >= 20 bits in the two extreme bands (the
+    // compiler if-converted a `1.0 / x` fallback, i.e. every call paid for a full IEEE division as well)
+    const unsigned ex = (unsigned)__double2hiint(x) & 0x7ff00000u;
+    return (ex - 0x04000000u < 0x78000000u) ? r : r0;
+#endif
 #endif
 }
 

@@ -106,17 +106,24 @@ struct MorrisLecarDev {  // examples/morris_lecar.jl:8-28
     template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(0); }
     template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
     // The CHV field (F, 1) / Rtot with the total rate written for the integrator: the two potassium rates are
-    // beta_k exp(+-(gamma_k v + k_k)), so ONE exponential and its reciprocal serve both (2 exp per stage instead
+    // beta_k exp(+-(gamma_k v + k_k)), so ONE exponential serves both (2 exp per stage instead
     // of 3; the value differs from the three-exponential sum in the last bits only).  The rates used for the
     // categorical draw at a jump (`rates` above) keep the reference's three separate exponentials.
     template <class R> PDMP_DEV static void chv_field(R* dy, const R* y, const int* xd, const double* p) {
         const R v = y[0];
         const R e_na = exp(R(4) * R(p[gamma_na]) * v + R(4) * R(p[k_na]));
         const R e_k = exp(R(p[gamma_k]) * v + R(p[k_k]));
+#ifdef PDMP_ML_TWO_RCP
         const R e_ki = rcp_fast(e_k);
         const R tot = ((R(p[beta_na]) * e_na * (R)xd[0] + R(p[beta_na]) * (R)xd[1]) + R(p[beta_k]) * e_k * (R)xd[2]) +
                       R(p[beta_k]) * e_ki * (R)xd[3];
         const R inv = rcp_fast(tot);
+#else
+        // 1 / tot = e_k / (e_k tot): the term in 1 / e_k becomes a constant, one reciprocal instead of two on the
+        // dependent path exp -> total rate -> field
+        const R part = (R(p[beta_na]) * e_na * (R)xd[0] + R(p[beta_na]) * (R)xd[1]) + R(p[beta_k]) * e_k * (R)xd[2];
+        const R inv = e_k * rcp_fast(part * e_k + R(p[beta_k]) * (R)xd[3]);
+#endif
         R f[1];
         F(f, y, xd, p, y[1]);
         dy[0] = f[0] * inv;
