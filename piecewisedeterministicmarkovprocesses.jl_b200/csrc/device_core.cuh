@@ -44,6 +44,17 @@ PDMP_DEV double rcp_fast(double x) {
 #endif
 }
 
+// a / b for operands of moderate size (no scaling for results near the overflow / underflow thresholds): Markstein's
+// residual correction of a * (1 / b), the correctly rounded quotient except in rare last-bit cases.  Unlike the
+// compiler's division it has no slow path — `0.0 / b` (an empty channel population over its size) sends the built-in
+// sequence into its ~60-instruction subroutine every time.
+PDMP_DEV double div_fast(double a, double b) {
+    const double r = rcp_fast(b);
+    const double q = a * r;
+    return fma(fma(-q, b, a), r, q);
+}
+PDMP_DEV float div_fast(float a, float b) { return a / b; }
+
 // error weights abstol + |u| reltol (positive, normal range) only feed the step controller, whose
 // powers are FP32 anyway: the bare MUFU.RCP64H seed (>= 20 mantissa bits, PTX rcp.approx.ftz.f64)
 // is enough — a relative error of 1e-6 in EEst moves an accept/reject decision only when EEst

@@ -89,8 +89,8 @@ struct MorrisLecarDev {  // examples/morris_lecar.jl:8-28
     static constexpr int SCHED_JUMP = 6, SCHED_REFILL = 2;    // ~2 expensive RK attempts (18 exp) per jump
     enum { v_Na, g_Na, v_K, g_K, v_L, g_L, I_app, gamma_na, k_na, beta_na, gamma_k, k_k, beta_k, M, N };
     template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
-        dx[0] = (R)xd[1] / R(p[N]) * (R(p[g_Na]) * (R(p[v_Na]) - x[0])) +
-                (R)xd[3] / R(p[M]) * (R(p[g_K]) * (R(p[v_K]) - x[0])) + (R(p[g_L]) * (R(p[v_L]) - x[0])) + R(p[I_app]);
+        dx[0] = div_fast((R)xd[1], R(p[N])) * (R(p[g_Na]) * (R(p[v_Na]) - x[0])) +
+                div_fast((R)xd[3], R(p[M])) * (R(p[g_K]) * (R(p[v_K]) - x[0])) + (R(p[g_L]) * (R(p[v_L]) - x[0])) + R(p[I_app]);
     }
     template <class R> PDMP_DEV static void rates(R* r, const R* x, const int* xd, const double* p, R t) {
         r[0] = R(p[beta_na]) * exp(R(4) * R(p[gamma_na]) * x[0] + R(4) * R(p[k_na])) * (R)xd[0];
