@@ -59,7 +59,7 @@ struct Tcp2dDev {  // examples/tcp2d.jl:4-25
     static constexpr int NC = 2, ND = 2, NR = 2, NP = 1;
     static constexpr bool HAS_BOUND = false, HAS_DELTA = false, ZERO_FLOW = false, HAS_CHV_FIELD = false;
     static constexpr const char* NAME = "tcp2d";
-    static constexpr int SCHED_JUMP = 16, SCHED_REFILL = 8;   // short trajectories: batch the initialisations
+    static constexpr int SCHED_JUMP = 16, SCHED_REFILL = 4;   // short trajectories: batch the initialisations (sweep: profiles/r2_sched_sweep_c.txt)
     template <class R> PDMP_DEV static void F(R* dx, const R* x, const int* xd, const double* p, R t) {
         if ((xd[0] & 1) == 0) { dx[0] = R(1); dx[1] = R(-1) * x[1]; }
         else { dx[0] = R(-1) * x[0]; dx[1] = R(1); }

@@ -179,6 +179,21 @@ def test_multi_device_two_gpus(G):
     _multi_case(G, list(range(G.device_count())))
 
 
+def test_empty_ensemble_and_empty_shards(G, orc):
+    """Ragged edge of the sharding: zero trajectories, and fewer trajectories than shards (empty shards)."""
+    pb = G.models.problem("tcp", tspan=(0.0, 5.0))
+    e = G.solve(pb, G.CHVGPU("tcp"), trajectories=0, n_jumps=10, seed=1)
+    c = orc.solve(pb, "tcp", algorithm="chv", ode="dp5", trajectories=0, n_jumps=10, seed=1)
+    assert list(e.offsets) == [0] == list(c.offsets) and len(e.time) == 0 and len(e.status) == 0
+    assert e.counters["total_jumps"] == 0
+    one = G.solve(pb, G.CHVGPU("tcp"), trajectories=2, n_jumps=50, seed=5, sample_times=[5.0])
+    many = G.solve(pb, G.CHVGPU("tcp"), trajectories=2, n_jumps=50, seed=5, sample_times=[5.0], devices=[0, 0, 0])
+    assert [b.n_traj for b in many.blocks] == [0, 1, 1] or sorted(b.n_traj for b in many.blocks) == [0, 1, 1]
+    for name in ("offsets", "time", "xc", "xd", "njumps", "status"):
+        assert np.array_equal(getattr(many, name), getattr(one, name)), name
+    assert np.array_equal(many.stat_count, one.stat_count)
+
+
 def test_multi_device_errors(G):
     pb = G.models.problem("tcp", tspan=(0.0, 5.0))
     with pytest.raises(G.PDMPError) as ei:
