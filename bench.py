@@ -260,7 +260,7 @@ def run_gpu(args):
                       "note": "rank 0's GPU only; tstop_policy 0 = OrdinaryDiffEq's h_clipped/q after a step clipped by a threshold"}
         e0.close(); del e0
     ens = mk(n, ics)
-    n_chunks = 1 if n <= 2 * (1 << 20) else -(-n // (1 << 20))
+    n_chunks = 1 if n <= 2 * (1 << 19) else -(-n // (1 << 19))
     stats_t, hist_t = P.distributed.stats_tensors(ens, dev)   # zero-copy torch views of the library's buffers
     stream = torch.cuda.current_stream().cuda_stream
 
