@@ -194,6 +194,24 @@ def test_empty_ensemble_and_empty_shards(G, orc):
     assert np.array_equal(many.stat_count, one.stat_count)
 
 
+def test_replay_stream_length_edges(G, orc):
+    """A replay stream that ends anywhere around the last draws a trajectory needs: same status, same saved points as the
+    oracle for every length (the CHV kernels draw ahead of use; a draw they never consume must not count as missing,
+    and the overshoot threshold needs ONE draw, a jump TWO)."""
+    u = np.random.default_rng(11).random(64)
+    for model, tf, nj in (("tcp", 3.0, 40), ("tcp", 1e5, 6), ("pdmp_stiff", 0.8, 40)):
+        pb = G.models.problem(model, tspan=(0.0, tf)) if model == "tcp" else G.models.problem(model, tspan=(0.322156, 0.322156 + tf))
+        seen = set()
+        for L in range(1, 30):
+            g = G.solve(pb, G.CHVGPU(model), n_jumps=nj, replay=u[None, :L])
+            c = orc.solve(pb, model, algorithm="chv", ode="dp5", n_jumps=nj, replay=u[None, :L])
+            assert g.status[0] == c.status[0], (model, tf, L)
+            assert np.array_equal(g.offsets, c.offsets) and np.array_equal(g.xd, c.xd) and np.array_equal(g.njumps, c.njumps), (model, tf, L)
+            assert np.allclose(g.time, c.time, rtol=1e-6, atol=1e-9), (model, tf, L)
+            seen.add(int(g.status[0]))
+        assert G._abi.ST_REPLAY_EXHAUSTED in seen and len(seen) >= 2, (model, seen)
+
+
 def test_multi_device_errors(G):
     pb = G.models.problem("tcp", tspan=(0.0, 5.0))
     with pytest.raises(G.PDMPError) as ei:
