@@ -100,6 +100,20 @@ template <class M, class = void> struct ChvSigned { static constexpr bool value 
 template <class M> struct ChvSigned<M, decltype((void)M::CHV_SIGNED_SCALAR)> { static constexpr bool value = M::CHV_SIGNED_SCALAR; };
 #endif
 
+// models that keep sub-expressions of the rates for the field at the post-jump state (`HAS_JUMP_CACHE`,
+// `JumpCache<R>`, `rates_cached`, `chv_field_cached`): used when the jump leaves xc unchanged (no Delta)
+template <class M, class = void> struct JumpCacheOk { static constexpr bool value = false; };
+template <class M> struct JumpCacheOk<M, decltype((void)M::HAS_JUMP_CACHE)> {
+#ifdef PDMP_NO_JUMP_CACHE
+    static constexpr bool value = false;
+#else
+    static constexpr bool value = M::HAS_JUMP_CACHE && M::HAS_CHV_FIELD && !M::HAS_DELTA;
+#endif
+};
+
+template <class M, class R, bool = JumpCacheOk<M>::value> struct JumpCacheOf { struct type {}; };
+template <class M, class R> struct JumpCacheOf<M, R, true> { using type = typename M::template JumpCache<R>; };
+
 // models whose F does not depend on (xc, t) between jumps (TCP: F = +-1): the plain-F flow is exact
 template <class M, class = void> struct ConstFlow { static constexpr bool value = false; };
 template <class M> struct ConstFlow<M, decltype((void)M::CONST_FLOW)> { static constexpr bool value = M::CONST_FLOW; };
@@ -454,7 +468,9 @@ struct Traj {
         bool ex = false;
         const double tj = threshold_time();
         R rate[NR];
-        M::rates(rate, y, xd, P.parms, (R)tj);  // :51, rates at the PRE-jump state
+        [[maybe_unused]] typename JumpCacheOf<M, R>::type jc;
+        if constexpr (JumpCacheOk<M>::value) M::rates_cached(rate, y, xd, P.parms, (R)tj, jc);
+        else M::rates(rate, y, xd, P.parms, (R)tj);  // :51, rates at the PRE-jump state
         R tot = rate[0];
 #pragma unroll
         for (int i = 1; i < NR; ++i) tot += rate[i];  // sum(rate), left to right
@@ -485,7 +501,9 @@ struct Traj {
             if constexpr (M::HAS_DELTA) M::delta(y, xd, P.parms, tj, ev);
             ev_done = ev;
             refresh_rate(P, tj);
-            field(P, y, k1, (R)tstop);  // u_modified!(integrator, true): FSAL re-evaluated (s = tstop here)
+            // u_modified!(integrator, true): FSAL re-evaluated (s = tstop here)
+            if constexpr (JumpCacheOk<M>::value) M::chv_field_cached(k1, y, xd, P.parms, jc);
+            else field(P, y, k1, (R)tstop);
 #pragma unroll
             for (int i = 0; i < NC; ++i) xs[i] = y[i];  // caract.xc .= u
             ts = tj;

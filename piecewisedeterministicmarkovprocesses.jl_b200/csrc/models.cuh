@@ -105,14 +105,31 @@ struct MorrisLecarDev {  // examples/morris_lecar.jl:8-28
     }
     template <class R> PDMP_DEV static R bound(const R* x, const int* xd, const double* p, R t) { return R(0); }
     template <class R> PDMP_DEV static void delta(R* x, int* xd, const double* p, double t, int ev) {}
+    // Jump cache (optional hook, HAS_JUMP_CACHE): a jump changes xd only, so the field at the post-jump state needs
+    // the same two exponentials of v the rates at the pre-jump state have just evaluated — the same expressions, the
+    // same values; the threshold section keeps them instead of calling exp twice more.
+    static constexpr bool HAS_JUMP_CACHE = true;
+    template <class R> struct JumpCache { R e_na, e_k; };
+    template <class R> PDMP_DEV static void rates_cached(R* r, const R* x, const int* xd, const double* p, R t, JumpCache<R>& c) {
+        c.e_na = exp(R(4) * R(p[gamma_na]) * x[0] + R(4) * R(p[k_na]));
+        c.e_k = exp(R(p[gamma_k]) * x[0] + R(p[k_k]));
+        r[0] = R(p[beta_na]) * c.e_na * (R)xd[0];
+        r[1] = R(p[beta_na]) * (R)xd[1];
+        r[2] = R(p[beta_k]) * c.e_k * (R)xd[2];
+        r[3] = R(p[beta_k]) * exp(-R(p[gamma_k]) * x[0] - R(p[k_k])) * (R)xd[3];
+    }
+    template <class R> PDMP_DEV static void chv_field_cached(R* dy, const R* y, const int* xd, const double* p, const JumpCache<R>& c) {
+        chv_field_from(dy, y, xd, p, c.e_na, c.e_k);
+    }
     // The CHV field (F, 1) / Rtot with the total rate written for the integrator: the two potassium rates are
     // beta_k exp(+-(gamma_k v + k_k)), so ONE exponential serves both (2 exp per stage instead
     // of 3; the value differs from the three-exponential sum in the last bits only).  The rates used for the
     // categorical draw at a jump (`rates` above) keep the reference's three separate exponentials.
     template <class R> PDMP_DEV static void chv_field(R* dy, const R* y, const int* xd, const double* p) {
         const R v = y[0];
-        const R e_na = exp(R(4) * R(p[gamma_na]) * v + R(4) * R(p[k_na]));
-        const R e_k = exp(R(p[gamma_k]) * v + R(p[k_k]));
+        chv_field_from(dy, y, xd, p, exp(R(4) * R(p[gamma_na]) * v + R(4) * R(p[k_na])), exp(R(p[gamma_k]) * v + R(p[k_k])));
+    }
+    template <class R> PDMP_DEV static void chv_field_from(R* dy, const R* y, const int* xd, const double* p, const R e_na, const R e_k) {
 #ifdef PDMP_ML_TWO_RCP
         const R e_ki = rcp_fast(e_k);
         const R tot = ((R(p[beta_na]) * e_na * (R)xd[0] + R(p[beta_na]) * (R)xd[1]) + R(p[beta_k]) * e_k * (R)xd[2]) +
