@@ -135,15 +135,29 @@ struct MorrisLecarDev {  // examples/morris_lecar.jl:8-28
         const R tot = ((R(p[beta_na]) * e_na * (R)xd[0] + R(p[beta_na]) * (R)xd[1]) + R(p[beta_k]) * e_k * (R)xd[2]) +
                       R(p[beta_k]) * e_ki * (R)xd[3];
         const R inv = rcp_fast(tot);
-#else
+#elif defined(PDMP_ML_PLAIN_FIELD)
         // 1 / tot = e_k / (e_k tot): the term in 1 / e_k becomes a constant, one reciprocal instead of two on the
         // dependent path exp -> total rate -> field
         const R part = (R(p[beta_na]) * e_na * (R)xd[0] + R(p[beta_na]) * (R)xd[1]) + R(p[beta_k]) * e_k * (R)xd[2];
         const R inv = e_k * rcp_fast(part * e_k + R(p[beta_k]) * (R)xd[3]);
+#else
+        // 1 / tot = e_k / (e_k tot): the term in 1 / e_k becomes a constant, one reciprocal instead of two on the
+        // dependent path exp -> total rate -> field.  Everything that depends on (xd, p) only is grouped into
+        // coefficients — loop-invariant over the stages of an RK phase, the compiler hoists them — so that a stage
+        // is 3 DFMA for the total rate and 1 for F = a - b v.
+        const R c0 = R(p[beta_na]) * (R)xd[0], c1 = R(p[beta_na]) * (R)xd[1], c2 = R(p[beta_k]) * (R)xd[2], c3 = R(p[beta_k]) * (R)xd[3];
+        const R inv = e_k * rcp_fast(fma(fma(c2, e_k, fma(c0, e_na, c1)), e_k, c3));
 #endif
+#if defined(PDMP_ML_TWO_RCP) || defined(PDMP_ML_PLAIN_FIELD)
         R f[1];
         F(f, y, xd, p, y[1]);
         dy[0] = f[0] * inv;
+#else
+        const R g_na = div_fast((R)xd[1], R(p[N])) * R(p[g_Na]), g_k = div_fast((R)xd[3], R(p[M])) * R(p[g_K]);
+        const R b = (g_na + g_k) + R(p[g_L]);
+        const R a = fma(g_na, R(p[v_Na]), fma(g_k, R(p[v_K]), fma(R(p[g_L]), R(p[v_L]), R(p[I_app]))));
+        dy[0] = fma(-b, y[0], a) * inv;
+#endif
         dy[1] = inv;
     }
 };
