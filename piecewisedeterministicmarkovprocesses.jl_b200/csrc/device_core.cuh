@@ -38,8 +38,14 @@ PDMP_DEV double rcp_fast(double x) {
     // outside 2^-959 <= |x| < 2^961 the Newton steps could overflow / produce NaN: keep the bare seed there, which is
     // already the right answer for 0 (inf), inf (0) and NaN, and good to >= 20 bits in the two extreme bands (the
     // compiler if-converted a `1.0 / x` fallback, i.e. every call paid for a full IEEE division as well)
+#ifdef PDMP_RCP_BAND_GUARD
     const unsigned ex = (unsigned)__double2hiint(x) & 0x7ff00000u;
     return (ex - 0x04000000u < 0x78000000u) ? r : r0;
+#else
+    // every input the Newton steps cannot handle (0, inf, NaN, subnormals flushed to 0 by the seed) turns them
+    // into NaN, and the seed is then the answer: one compare instead of the exponent-band test
+    return r == r ? r : r0;
+#endif
 #endif
 #endif
 }
