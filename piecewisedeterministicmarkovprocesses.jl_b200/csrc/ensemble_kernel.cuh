@@ -589,6 +589,9 @@ struct Traj {
 #ifndef PDMP_MINB_MEDIUM
 #define PDMP_MINB_MEDIUM 5
 #endif
+#ifndef PDMP_MINB_NOFLOW
+#define PDMP_MINB_NOFLOW 8
+#endif
 #ifndef PDMP_MINB_LARGE
 #define PDMP_MINB_LARGE 4
 #endif
@@ -597,7 +600,11 @@ struct MinBlocks {
     static constexpr int D = (ALG == PDMP_ALG_CHV) ? M::NC + 1 : M::NC;
     static constexpr bool small = (D <= 2 && M::NR <= 2 && M::ND <= 2);
     static constexpr bool medium = (D <= 3 && M::NR <= 2 && M::ND <= 2);   // tcp2d: 96 registers, measured +8 %
-    static constexpr int value = sizeof(R) == 4 ? (small ? 7 : 5) : (small ? (M::HAS_CHV_FIELD ? PDMP_MINB_SMALL : 6) : medium ? PDMP_MINB_MEDIUM : PDMP_MINB_LARGE);
+    // Rejection with F = F_dummy: no RK state at all, the kernel only runs the candidate section and is latency-bound
+    // (Philox -> log -> two divisions): as many resident warps as the register file gives
+    static constexpr bool no_flow = (ALG == PDMP_ALG_REJECTION) && M::ZERO_FLOW;
+    static constexpr int value = no_flow ? PDMP_MINB_NOFLOW
+                                 : sizeof(R) == 4 ? (small ? 7 : 5) : (small ? (M::HAS_CHV_FIELD ? PDMP_MINB_SMALL : 6) : medium ? PDMP_MINB_MEDIUM : PDMP_MINB_LARGE);
 };
 
 // lane states of the phase scheduler
