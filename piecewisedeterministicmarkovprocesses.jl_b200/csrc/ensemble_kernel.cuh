@@ -581,13 +581,13 @@ struct Traj {
 // registers), those with a hand-simplified CHV field (TCP) 7 x 128 (<= 72 registers, no spills; measured on
 // TCP with the final round-2 kernel, 4 M trajectories: 6 CTAs 34.4 ms, 7 CTAs 34.2 ms, 8 CTAs / 64 registers
 // with 174 spilled bytes 35.4 ms, 9 CTAs 35.0 ms; 10^7 trajectories: 76.4 / 76.3 / 77.6 ms — earlier in the
-// round, with a longer loop, 8 had been ahead), medium ones 5 (<= 96), the larger ones 4 (<= 128
+// round, with a longer loop, 8 had been ahead), medium ones 6 (<= 80; tcp2d 4 / 5 / 6 CTAs: 16.5 / 14.95 / 14.63 ms), the larger ones 4 (<= 128
 // registers; Morris-Lecar loses 10 % to spills at 96)
 #ifndef PDMP_MINB_SMALL
 #define PDMP_MINB_SMALL 7
 #endif
 #ifndef PDMP_MINB_MEDIUM
-#define PDMP_MINB_MEDIUM 5
+#define PDMP_MINB_MEDIUM 6
 #endif
 #ifndef PDMP_MINB_NOFLOW
 #define PDMP_MINB_NOFLOW 8
